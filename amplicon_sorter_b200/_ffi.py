@@ -1,0 +1,70 @@
+"""ctypes binding of include/asb200.h.  There is no fallback: a missing library is a hard error."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+RECORD = np.dtype([("i_pos", "<u4"), ("j_pos", "<u4"), ("d", "<u4"), ("reverse", "<u4")])
+
+ASB_OK, ASB_DONE = 0, 1
+
+
+class StepInfo(C.Structure):
+    _fields_ = [("pairs", C.c_uint64), ("n_records", C.c_uint64), ("fwd_survivors", C.c_uint64),
+                ("rc_survivors", C.c_uint64), ("zone_checks", C.c_uint64), ("word_updates", C.c_uint64),
+                ("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("screen_ms", C.c_float), ("total_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"asb200 error {code}: {msg}")
+        self.code = code
+
+
+_LIB = None
+
+SYMBOLS = ["asb_version", "asb_create", "asb_destroy", "asb_last_error", "asb_set_param", "asb_upload_reads",
+           "asb_batch_begin", "asb_batch_step", "asb_batch_records", "asb_distance_pairs", "asb_debug_read"]
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load libasb200.so (built in-tree by build.py / __graft_entry__.build()).  Raises if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise EngineError(-100, f"{path} is missing: run `python -m amplicon_sorter_b200.build` "
+                                "(the CUDA library is the product; there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, u8p, u32p, u64p, i32p = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)
+    L.asb_version.restype = C.c_int
+    L.asb_create.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.asb_destroy.argtypes = [vp]
+    L.asb_destroy.restype = None
+    L.asb_last_error.argtypes = [vp]
+    L.asb_last_error.restype = C.c_char_p
+    L.asb_set_param.argtypes = [vp, C.c_char_p, C.c_double]
+    L.asb_upload_reads.argtypes = [vp, u8p, u64p, C.c_uint32]
+    L.asb_batch_begin.argtypes = [vp, u32p, C.c_uint32, u32p, u32p, u32p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.asb_batch_step.argtypes = [vp, C.POINTER(StepInfo)]
+    L.asb_batch_records.argtypes = [vp, vp]
+    L.asb_distance_pairs.argtypes = [vp, u32p, u32p, u8p, C.c_uint64, C.c_int, i32p]
+    L.asb_debug_read.argtypes = [vp, C.c_uint32, C.c_int, u8p, C.c_uint32]
+    _LIB = L
+    return L
+
+
+def ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(C.POINTER(t))

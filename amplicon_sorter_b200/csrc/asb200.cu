@@ -1,0 +1,866 @@
+// asb200.cu -- kernels + C ABI of the B200 all-pairs read-similarity engine (see include/asb200.h).
+//
+// Path replaced (all /root/reference/amplicon_sorter.py): process_list.queuer :662-715 (pair
+// enumeration, length window), similarity :776-807 (three-way rule), distance :224-234
+// (edlib NW distance), compl_reverse :236-241.
+//
+// Pipeline per slab of rows ("step"):
+//   asb_screen   every kept pair (i<j<=hi[i]): banded pass (k = dpass[len_j]) on the forward strand
+//                with early termination; pairs proven d_fwd > dpass get the same pass on the
+//                compl_reverse strand.  Undecided pairs go to the F / R lists.
+//   asb_lists    F: full forward pass  -> emit, or (d_fwd > dpass) -> R
+//                R: full reverse pass  -> (d_rc <= dpass) -> Z
+//                Z: forward pass with k = drev-1 -> emit ':reverse' iff d_fwd >= drev
+//   The reference decides "iden_fwd < 0.5" BEFORE trying the reverse strand; we try the (cheap)
+//   reverse strand first and only pay for the exact forward decision on the few pairs where it
+//   can change the output.  The emitted set is identical by construction.
+//   cub radix sorts put the lists in (row, column) order so that the 32 lanes of a warp share a
+//   query, and put the emitted records in the reference's line order.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cuda_runtime.h>
+
+#include "../../include/asb200.h"
+#include "myers_band.cuh"
+
+namespace asb {
+
+// --------------------------------------------------------------------------------------------
+// device-side views
+// --------------------------------------------------------------------------------------------
+enum Counter : int { C_TASK = 0, C_F, C_R, C_Z, C_O, C_WORDS, C_ERR, C_COUNT };
+enum Mode : int { M_SCREEN = 0, M_FWD = 1, M_RC = 2, M_ZONE = 3, M_EXACT = 4 };
+enum DevErr : unsigned long long { E_BAND = 1ull, E_TABLE = 2ull, E_LIST = 4ull };
+
+struct DevBatch {
+    const uint8_t* codes_f;   // forward symbol codes, read regions 32-byte aligned + padded
+    const uint8_t* codes_r;   // compl_reverse symbol codes, same offsets
+    const uint64_t* pos_off;  // [n] code offset of the read at sorted position p
+    const uint32_t* pos_len;  // [n] its length
+    const uint32_t* hi;       // [n] last kept partner position of row p
+    const uint32_t* dpass;    // [table_len]
+    const uint32_t* drev;     // [table_len]
+    uint32_t table_len, n, sigma;
+    int Wpad;                 // shared-memory stride of one Peq row (odd, >= W + window)
+    uint64_t* F; uint64_t* R; uint64_t* Z; uint32_t* Zv; uint64_t* O; uint32_t* Ov;
+    unsigned long long* ctr;  // [C_COUNT]
+    uint64_t list_cap;
+    // screen task space
+    const uint32_t* grp_prefix;  // [rows+1] prefix of 32-target groups per row of the step
+    uint32_t row_begin, rows;
+    uint32_t n_tasks, rank, world;
+    int screen_cols_num;  // screen runs at most ceil(nmax * num / 256) columns
+    int push_thresh;
+    // list task space
+    const uint64_t* list; const uint32_t* list_val; uint64_t list_n;
+    const uint8_t* ex_strand; int32_t* ex_out;  // M_EXACT
+};
+
+__device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+// warp-aggregated append; returns nothing, drops silently (and flags) past capacity
+__device__ __forceinline__ void warp_push(bool pred, uint64_t* keys, uint32_t* vals, unsigned long long* cnt, uint64_t cap,
+                                          uint64_t key, uint32_t val, unsigned long long* err)
+{
+    const unsigned mask = __ballot_sync(0xFFFFFFFFu, pred);
+    if (mask == 0u) return;
+    const int leader = __ffs(mask) - 1;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(cnt, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    if (pred) {
+        const unsigned long long idx = base + __popc(mask & lanemask_lt());
+        if (idx < cap) { keys[idx] = key; if (vals) vals[idx] = val; }
+        else atomicOr(err, (unsigned long long)E_LIST);
+    }
+}
+
+// Match masks of the query at sorted position `row` into this warp's shared-memory table.
+// Lane l owns words l, l+32, ...; bit b of word w of row `sym` <=> query[32w+b] == sym.
+__device__ __forceinline__ void build_peq(uint32_t* peq, const DevBatch& B, const uint8_t* q, int m, int W)
+{
+    const int lane = threadIdx.x & 31;
+    const int words = (B.sigma + 1) * B.Wpad;
+    for (int x = lane; x < words; x += 32) peq[x] = 0u;
+    __syncwarp();
+    for (int w = lane; w < W; w += 32) {
+        const uint4* src = reinterpret_cast<const uint4*>(q + 32 * w);
+        const uint4 a = __ldg(src), b = __ldg(src + 1);
+        const uint32_t cw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const int lim = min(32, m - 32 * w);
+#pragma unroll
+        for (int p = 0; p < 32; ++p) {
+            if (p < lim) {
+                const uint32_t sym = (cw[p >> 2] >> (8 * (p & 3))) & 0xFFu;
+                peq[sym * B.Wpad + w] |= 1u << p;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+struct LaneJob {
+    bool valid;      // lane holds a pair
+    uint32_t j;      // target position
+    uint32_t zval;   // M_ZONE: d_rc carried by the entry
+    uint64_t entry;  // M_EXACT: output slot
+    int strand;      // M_EXACT
+};
+
+// All lanes with valid==true share query `row`.  Runs the mode's passes and routes the results.
+template <int BT>
+__device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, const int mode, const uint32_t row,
+                                              const LaneJob job, unsigned long long& cols_acc)
+{
+    const int m = (int)B.pos_len[row];
+    const uint8_t* q = B.codes_f + B.pos_off[row];
+    const int W = (m + 31) >> 5;
+    int n = m, k = -1;
+    bool ok = job.valid;
+    const uint8_t* tf = q;
+    const uint8_t* tr = q;
+    if (job.valid) {
+        n = (int)B.pos_len[job.j];
+        const uint64_t off = B.pos_off[job.j];
+        tf = B.codes_f + off;
+        tr = B.codes_r + off;
+        if (mode == M_EXACT) k = n;
+        else if ((uint32_t)n >= B.table_len) { atomicOr(&B.ctr[C_ERR], (unsigned long long)E_TABLE); ok = false; }
+        else if (mode == M_ZONE) k = (int)B.drev[n] - 1;
+        else { const uint32_t kk = B.dpass[n]; k = kk == 0xFFFFFFFFu ? -1 : (int)kk; }
+        if (n - m > k) ok = false;  // d >= n-m > k on either strand
+    }
+    const uint64_t key = ((uint64_t)row << 32) | job.j;
+    if (m == 0) {  // empty query: d = n, no DP needed (never happens behind -min 300)
+        const bool pass = ok && n <= k;
+        if (mode == M_SCREEN || mode == M_FWD) warp_push(pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, ((uint32_t)n << 1), &B.ctr[C_ERR]);
+        if (mode == M_ZONE) warp_push(job.valid && !pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, (job.zval << 1) | 1u, &B.ctr[C_ERR]);
+        if (mode == M_EXACT && job.valid) B.ex_out[job.entry] = n;
+        return;
+    }
+    // ---- warp-uniform band geometry covering every participating lane
+    const int e = ok ? (k - (n - m)) >> 1 : 0;
+    const int Dmax = __reduce_max_sync(0xFFFFFFFFu, ok ? (n - m) + e : 0);
+    const int Emax = __reduce_max_sync(0xFFFFFFFFu, e);
+    const int nmax = __reduce_max_sync(0xFFFFFFFFu, ok ? n : 0);
+    const unsigned okm = __ballot_sync(0xFFFFFFFFu, ok);
+    if (okm == 0u) {
+        if (mode == M_ZONE) warp_push(job.valid, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, (job.zval << 1) | 1u, &B.ctr[C_ERR]);
+        return;
+    }
+    BandGeom g;
+    g.BL = (Dmax + 31) >> 5;
+    const int need = g.BL + ((Emax + 31) >> 5) + 1;
+    g.Bw = BT > 0 ? BT : min(need, max(W, 1));
+    if ((BT > 0 && need > BT && W > BT) || (BT == 0 && g.Bw > kMaxDynWords)) {
+        atomicOr(&B.ctr[C_ERR], (unsigned long long)E_BAND);
+        return;
+    }
+    const int full_cols = (nmax + 31) & ~31;
+    g.ncols = full_cols;
+    int push = 0;
+    if (mode == M_SCREEN) {
+        const int lim = (((nmax * B.screen_cols_num) >> 8) + 31) & ~31;
+        g.ncols = min(full_cols, max(lim, 32));
+        push = B.push_thresh;
+    }
+    build_peq(peq, B, q, m, W);
+
+    int st, sc;
+    if (mode == M_SCREEN || mode == M_FWD || mode == M_ZONE || mode == M_EXACT) {
+        const uint8_t* t = (mode == M_EXACT && job.strand) ? tr : tf;
+        band_pass<BT>(peq, B.Wpad, W, m, t, n, k, ok, g, push, st, sc, cols_acc);
+        if (mode == M_EXACT) {
+            if (job.valid) B.ex_out[job.entry] = (st == PASS_DONE) ? sc : -1;
+            return;
+        }
+        const bool pass = ok && st == PASS_DONE && sc <= k;
+        if (mode == M_ZONE) {  // emit the reverse record iff d_fwd > drev-1  (iden_fwd < 0.5, AS:794)
+            warp_push(job.valid && !pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, (job.zval << 1) | 1u, &B.ctr[C_ERR]);
+            return;
+        }
+        warp_push(pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, ((uint32_t)sc << 1), &B.ctr[C_ERR]);  // AS:791-793
+        const bool surv = ok && st == PASS_SURVIVOR;
+        if (mode == M_SCREEN) warp_push(surv, B.F, nullptr, &B.ctr[C_F], B.list_cap, key, 0u, &B.ctr[C_ERR]);
+        const bool need_rc = ok && !pass && !surv;  // proven d_fwd > dpass
+        if (mode == M_FWD) { warp_push(need_rc, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]); return; }
+        ok = need_rc;
+        if (__ballot_sync(0xFFFFFFFFu, ok) == 0u) return;
+    }
+    // ---- compl_reverse strand (AS:795): same band, k = dpass
+    band_pass<BT>(peq, B.Wpad, W, m, tr, n, k, ok, g, push, st, sc, cols_acc);
+    const bool rpass = ok && st == PASS_DONE && sc <= k;
+    warp_push(rpass, B.Z, B.Zv, &B.ctr[C_Z], B.list_cap, key, (uint32_t)sc, &B.ctr[C_ERR]);
+    if (mode == M_SCREEN) warp_push(ok && st == PASS_SURVIVOR, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]);
+}
+
+// --------------------------------------------------------------------------------------------
+// asb_screen: persistent warps pull (row, 32 consecutive targets) tasks from an atomic counter.
+// --------------------------------------------------------------------------------------------
+template <int BT>
+__global__ void __launch_bounds__(256) asb_screen(const DevBatch B)
+{
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* peq = smem + wid * ((B.sigma + 1) * B.Wpad);
+    unsigned long long cols_acc = 0;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&B.ctr[C_TASK], 1ull);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= B.n_tasks) break;
+        const uint32_t gidx = (uint32_t)t * B.world + B.rank;  // cyclic deal of groups over ranks
+        // row = last r with grp_prefix[r] <= gidx
+        uint32_t lo = 0, hi = B.rows;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&B.grp_prefix[mid]) <= gidx) lo = mid; else hi = mid;
+        }
+        const uint32_t row = B.row_begin + lo;
+        const uint32_t gi = gidx - __ldg(&B.grp_prefix[lo]);
+        LaneJob job;
+        job.j = row + 1 + gi * 32 + lane;
+        job.valid = job.j <= B.hi[row];
+        job.zval = 0; job.entry = 0; job.strand = 0;
+        process_group<BT>(B, peq, M_SCREEN, row, job, cols_acc);
+    }
+    if (lane == 0 && cols_acc) atomicAdd(&B.ctr[C_WORDS], cols_acc);
+}
+
+// --------------------------------------------------------------------------------------------
+// asb_lists: persistent warps pull 32-entry slices of a (row, column)-sorted list; a slice that
+// spans several rows is processed one row-run at a time.
+// --------------------------------------------------------------------------------------------
+template <int BT>
+__global__ void __launch_bounds__(256) asb_lists(const DevBatch B, const int mode)
+{
+    extern __shared__ uint32_t smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* peq = smem + wid * ((B.sigma + 1) * B.Wpad);
+    unsigned long long cols_acc = 0;
+    const unsigned long long n_slices = (B.list_n + 31) >> 5;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&B.ctr[C_TASK], 1ull);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= n_slices) break;
+        const uint64_t e = t * 32 + lane;
+        const bool have = e < B.list_n;
+        const uint64_t key = have ? B.list[e] : 0;
+        const uint32_t myrow = (uint32_t)(key >> 32);
+        bool pending = have;
+        for (;;) {
+            const unsigned pm = __ballot_sync(0xFFFFFFFFu, pending);
+            if (pm == 0u) break;
+            const uint32_t row = __shfl_sync(0xFFFFFFFFu, myrow, __ffs(pm) - 1);
+            LaneJob job;
+            job.valid = pending && myrow == row;
+            job.j = (uint32_t)key;
+            job.zval = (mode == M_ZONE && have) ? B.list_val[e] : 0u;
+            job.entry = e;
+            job.strand = (mode == M_EXACT && have) ? (int)B.ex_strand[e] : 0;
+            process_group<BT>(B, peq, mode, row, job, cols_acc);
+            pending = pending && !job.valid;
+        }
+    }
+    if (lane == 0 && cols_acc) atomicAdd(&B.ctr[C_WORDS], cols_acc);
+}
+
+// --------------------------------------------------------------------------------------------
+// K1: alphabet scan + symbol coding (forward and compl_reverse)
+// --------------------------------------------------------------------------------------------
+__global__ void asb_alpha_scan(const uint8_t* __restrict__ ascii, uint64_t nbytes, uint32_t* __restrict__ present /*[8]*/)
+{
+    __shared__ uint32_t bits[8];
+    if (threadIdx.x < 8) bits[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint8_t c = ascii[i];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) loc[w] |= ((c >> 5) == w) ? (1u << (c & 31)) : 0u;
+    }
+#pragma unroll
+    for (int w = 0; w < 8; ++w) if (loc[w]) atomicOr(&bits[w], loc[w]);
+    __syncthreads();
+    if (threadIdx.x < 8 && bits[threadIdx.x]) atomicOr(&present[threadIdx.x], bits[threadIdx.x]);
+}
+
+// one block per read; code_of[256] maps ASCII -> symbol code, comp[256] is compl_reverse's table
+__global__ void asb_encode(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ offs, const uint64_t* __restrict__ roff,
+                           uint32_t n_reads, const uint8_t* __restrict__ code_of, const uint8_t* __restrict__ comp, uint8_t pad,
+                           uint8_t* __restrict__ cf, uint8_t* __restrict__ cr)
+{
+    for (uint32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        const uint64_t a = offs[r], len = offs[r + 1] - a, o = roff[r];
+        const uint64_t region = roff[r + 1] - o;
+        for (uint64_t p = threadIdx.x; p < region; p += blockDim.x) {
+            uint8_t f = pad, v = pad;
+            if (p < len) {
+                f = code_of[ascii[a + p]];
+                v = code_of[comp[ascii[a + len - 1 - p]]];  // AS:240 self[::-1].translate(complement)
+            }
+            cf[o + p] = f;
+            cr[o + p] = v;
+        }
+    }
+}
+
+}  // namespace asb
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace asb;
+
+namespace {
+
+constexpr int kClasses[] = {3, 5, 7, 9, 11, 13, 15, 17, 20, 24, 28, 32, 36, 40, 0};
+constexpr int kNumClasses = sizeof(kClasses) / sizeof(int);
+constexpr int kWarpsPerBlock = 8;
+
+typedef void (*screen_fn)(const DevBatch);
+typedef void (*lists_fn)(const DevBatch, const int);
+
+template <int... Bs> struct FnTable {
+    static screen_fn screen(int idx) { static const screen_fn t[] = {asb_screen<Bs>...}; return t[idx]; }
+    static lists_fn lists(int idx) { static const lists_fn t[] = {asb_lists<Bs>...}; return t[idx]; }
+};
+using Fns = FnTable<3, 5, 7, 9, 11, 13, 15, 17, 20, 24, 28, 32, 36, 40, 0>;
+
+int class_for(int need)
+{
+    for (int i = 0; i < kNumClasses - 1; ++i) if (kClasses[i] >= need) return i;
+    return kNumClasses - 1;  // dynamic
+}
+
+template <typename T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(want, 1) * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct asb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int sm_count = 148;
+    // params
+    uint64_t pair_cap = 1ull << 26;
+    double screen_frac = 0.62;
+    int push_thresh = 3;
+    // reads
+    uint32_t n_reads = 0, sigma = 0, max_len = 0;
+    uint8_t code_to_ascii[257];
+    std::vector<uint64_t> h_roff;  // [n_reads+1] padded code offsets
+    std::vector<uint32_t> h_rlen;
+    DevBuf<uint8_t> d_cf, d_cr;
+    // batch
+    uint32_t n = 0, rank = 0, world = 1, table_len = 0;
+    std::vector<uint32_t> h_len, h_hi, h_dpass, h_drev;
+    std::vector<uint32_t> h_pmax_dpass, h_pmax_drev;  // prefix maxima of the tables
+    DevBuf<uint64_t> d_pos_off; DevBuf<uint32_t> d_pos_len, d_hi, d_dpass, d_drev, d_grp;
+    uint32_t next_row = 0;
+    bool in_batch = false;
+    // lists
+    DevBuf<uint64_t> d_F, d_R, d_Z, d_O, d_alt; DevBuf<uint32_t> d_Zv, d_Ov, d_altv;
+    DevBuf<unsigned long long> d_ctr;
+    DevBuf<uint8_t> d_tmp;
+    uint64_t list_cap = 0;
+    unsigned long long* h_ctr = nullptr;  // pinned [C_COUNT]
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // last step's sorted records on device
+    uint64_t* rec_keys = nullptr; uint32_t* rec_vals = nullptr; uint64_t rec_n = 0;
+    asb_record* h_stage = nullptr; size_t h_stage_n = 0;  // pinned staging
+    DevBuf<asb_record> d_rec;
+};
+
+namespace {
+
+int fail(asb_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? ASB_E_NOMEM : ASB_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+__global__ void asb_pack_records(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint64_t n, asb_record* __restrict__ out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint64_t k = keys[i]; const uint32_t v = vals[i];
+        asb_record r; r.i_pos = (uint32_t)(k >> 32); r.j_pos = (uint32_t)k; r.d = v >> 1; r.reverse = v & 1u;
+        out[i] = r;
+    }
+}
+
+int bits_for(uint32_t n) { int b = 0; while ((1ull << b) < (uint64_t)n + 1) ++b; return b; }
+
+// sort keys (and optional values) in place-ish with cub; result pointer returned through outs
+int sort_list(asb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t n, uint64_t** out_keys, uint32_t** out_vals)
+{
+    *out_keys = keys; if (out_vals) *out_vals = vals;
+    if (n <= 1) return ASB_OK;
+    const int end_bit = std::min(64, 32 + bits_for(ctx->n));
+    cub::DoubleBuffer<uint64_t> kb(keys, ctx->d_alt.p);
+    size_t tmp = 0;
+    if (vals) {
+        cub::DoubleBuffer<uint32_t> vb(vals, ctx->d_altv.p);
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
+        CU(ctx->d_tmp.ensure(tmp));
+        CU(cub::DeviceRadixSort::SortPairs(ctx->d_tmp.p, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
+        *out_vals = vb.Current();
+    } else {
+        CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, kb, (int64_t)n, 0, end_bit, ctx->stream));
+        CU(ctx->d_tmp.ensure(tmp));
+        CU(cub::DeviceRadixSort::SortKeys(ctx->d_tmp.p, tmp, kb, (int64_t)n, 0, end_bit, ctx->stream));
+    }
+    *out_keys = kb.Current();
+    return ASB_OK;
+}
+
+int ensure_lists(asb_ctx* ctx, uint64_t cap)
+{
+    if (cap <= ctx->list_cap) return ASB_OK;
+    CU(ctx->d_F.ensure(cap)); CU(ctx->d_R.ensure(cap)); CU(ctx->d_Z.ensure(cap)); CU(ctx->d_O.ensure(cap)); CU(ctx->d_alt.ensure(cap));
+    CU(ctx->d_Zv.ensure(cap)); CU(ctx->d_Ov.ensure(cap)); CU(ctx->d_altv.ensure(cap));
+    ctx->list_cap = cap;
+    return ASB_OK;
+}
+
+int read_counters(asb_ctx* ctx)
+{
+    CU(cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr.p, sizeof(unsigned long long) * C_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ctr[C_ERR]) {
+        const unsigned long long e = ctx->h_ctr[C_ERR];
+        if (e & E_BAND) return fail(ctx, ASB_E_TOO_LONG, "band wider than the engine supports (read too long for this threshold)");
+        if (e & E_TABLE) return fail(ctx, ASB_E_ARG, "read longer than the threshold tables (table_len)");
+        return fail(ctx, ASB_E_INTERNAL, "device error flags 0x%llx", e);
+    }
+    return ASB_OK;
+}
+
+size_t smem_bytes(const asb_ctx* ctx, int Wpad) { return (size_t)kWarpsPerBlock * (ctx->sigma + 1) * Wpad * sizeof(uint32_t); }
+
+template <typename F> int launch_cfg(asb_ctx* ctx, F fn, size_t smem, int* grid)
+{
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * 32, smem));
+    if (per_sm < 1) return fail(ctx, ASB_E_TOO_LONG, "kernel does not fit on an SM (shared memory %zu bytes)", smem);
+    *grid = per_sm * ctx->sm_count;
+    return ASB_OK;
+}
+
+int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint32_t* vals, uint64_t n)
+{
+    if (n == 0) return ASB_OK;
+    B.list = keys; B.list_val = vals; B.list_n = n;
+    CU(cudaMemsetAsync(ctx->d_ctr.p + C_TASK, 0, sizeof(unsigned long long), ctx->stream));
+    lists_fn fn = Fns::lists(cls);
+    const size_t smem = smem_bytes(ctx, B.Wpad);
+    int grid = 0;
+    int rc = launch_cfg(ctx, fn, smem, &grid);
+    if (rc) return rc;
+    const uint64_t slices = (n + 31) / 32, blocks = (slices + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    grid = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint64_t>(blocks, 1));
+    fn<<<grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(B, mode);
+    CU(cudaGetLastError());
+    return ASB_OK;
+}
+
+int odd_stride(int w) { return w | 1; }
+
+}  // namespace
+
+extern "C" {
+
+int asb_version(void) { return 100; }
+
+const char* asb_last_error(const asb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int asb_create(int device, void* stream, asb_ctx** out)
+{
+    if (!out) return ASB_E_ARG;
+    *out = nullptr;
+    asb_ctx* ctx = new (std::nothrow) asb_ctx();
+    if (!ctx) return ASB_E_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { delete ctx; return ASB_E_CUDA; }
+    if (stream) ctx->stream = (cudaStream_t)stream;
+    else { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * C_COUNT);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = ctx->d_ctr.ensure(C_COUNT);
+    if (e != cudaSuccess) { asb_destroy(ctx); return ASB_E_CUDA; }
+    *out = ctx;
+    return ASB_OK;
+}
+
+void asb_destroy(asb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->d_cf.release(); ctx->d_cr.release(); ctx->d_pos_off.release(); ctx->d_pos_len.release(); ctx->d_hi.release();
+    ctx->d_dpass.release(); ctx->d_drev.release(); ctx->d_grp.release(); ctx->d_F.release(); ctx->d_R.release(); ctx->d_Z.release();
+    ctx->d_O.release(); ctx->d_alt.release(); ctx->d_Zv.release(); ctx->d_Ov.release(); ctx->d_altv.release(); ctx->d_ctr.release();
+    ctx->d_tmp.release(); ctx->d_rec.release();
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int asb_set_param(asb_ctx* ctx, const char* name, double value)
+{
+    if (!ctx || !name) return ASB_E_ARG;
+    if (!strcmp(name, "pair_cap")) { if (value < 1024) return fail(ctx, ASB_E_ARG, "pair_cap too small"); ctx->pair_cap = (uint64_t)value; }
+    else if (!strcmp(name, "screen_frac")) { if (value <= 0 || value > 1) return fail(ctx, ASB_E_ARG, "screen_frac in (0,1]"); ctx->screen_frac = value; }
+    else if (!strcmp(name, "push_thresh")) { if (value < 0 || value > 31) return fail(ctx, ASB_E_ARG, "push_thresh in [0,31]"); ctx->push_thresh = (int)value; }
+    else return fail(ctx, ASB_E_ARG, "unknown parameter %s", name);
+    return ASB_OK;
+}
+
+int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint32_t n_reads)
+{
+    if (!ctx || !offs || (!ascii && n_reads && offs[n_reads])) return fail(ctx, ASB_E_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->in_batch = false;
+    const uint64_t nbytes = n_reads ? offs[n_reads] : 0;
+    ctx->n_reads = n_reads;
+    ctx->h_roff.assign((size_t)n_reads + 1, 0);
+    ctx->h_rlen.assign(n_reads, 0);
+    uint32_t max_len = 0;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        if (offs[r + 1] < offs[r] || offs[r + 1] - offs[r] > 0x7FFFFF00ull) return fail(ctx, ASB_E_ARG, "bad offsets at read %u", r);
+        const uint32_t len = (uint32_t)(offs[r + 1] - offs[r]);
+        ctx->h_rlen[r] = len;
+        max_len = std::max(max_len, len);
+        ctx->h_roff[r + 1] = ctx->h_roff[r] + (((uint64_t)len + 31) & ~31ull) + 64;  // 32-byte aligned regions + slack
+    }
+    ctx->max_len = max_len;
+    const uint64_t total = ctx->h_roff[n_reads] + (((uint64_t)max_len + 31) & ~31ull) + 128;  // over-read slack for short lanes
+    DevBuf<uint8_t> d_ascii; DevBuf<uint64_t> d_offs, d_roff; DevBuf<uint32_t> d_present; DevBuf<uint8_t> d_maps;
+    struct Guard { DevBuf<uint8_t>&a; DevBuf<uint64_t>&b,&c; DevBuf<uint32_t>&d; DevBuf<uint8_t>&e; ~Guard(){a.release();b.release();c.release();d.release();e.release();} } guard{d_ascii, d_offs, d_roff, d_present, d_maps};
+    CU(d_ascii.ensure(nbytes + 1)); CU(d_offs.ensure((size_t)n_reads + 1)); CU(d_roff.ensure((size_t)n_reads + 1));
+    CU(d_present.ensure(8)); CU(d_maps.ensure(512));
+    CU(ctx->d_cf.ensure(total)); CU(ctx->d_cr.ensure(total));
+    if (nbytes) CU(cudaMemcpyAsync(d_ascii.p, ascii, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_offs.p, offs, sizeof(uint64_t) * ((size_t)n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_roff.p, ctx->h_roff.data(), sizeof(uint64_t) * ((size_t)n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(d_present.p, 0, 32, ctx->stream));
+    if (nbytes) {
+        asb_alpha_scan<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_ascii.p, nbytes, d_present.p);
+        CU(cudaGetLastError());
+    }
+    uint32_t present[8];
+    CU(cudaMemcpyAsync(present, d_present.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    // compl_reverse's translation table (AS:237-239) and the alphabet closed under it
+    uint8_t maps[512];
+    uint8_t* code_of = maps; uint8_t* comp = maps + 256;
+    for (int i = 0; i < 256; ++i) comp[i] = (uint8_t)i;
+    { const char* a = "ATCGRYKMSW"; const char* b = "TAGCYRMKSW"; for (int i = 0; a[i]; ++i) comp[(uint8_t)a[i]] = (uint8_t)b[i]; }
+    bool has[256];
+    for (int i = 0; i < 256; ++i) has[i] = (present[i >> 5] >> (i & 31)) & 1u;
+    for (int i = 0; i < 256; ++i) if (has[i]) has[comp[i]] = true;  // comp is an involution on its support
+    uint32_t sigma = 0;
+    memset(code_of, 0, 256);
+    for (int i = 0; i < 256; ++i) if (has[i]) { if (sigma >= 255) return fail(ctx, ASB_E_ARG, "alphabet of 256 symbols is not supported"); ctx->code_to_ascii[sigma] = (uint8_t)i; code_of[i] = (uint8_t)sigma++; }
+    ctx->sigma = sigma;
+    ctx->code_to_ascii[sigma] = 0;
+    CU(cudaMemcpyAsync(d_maps.p, maps, 512, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cf.p, (int)sigma, total, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cr.p, (int)sigma, total, ctx->stream));
+    if (n_reads) {
+        asb_encode<<<std::min<uint32_t>(n_reads, (uint32_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
+            d_ascii.p, d_offs.p, d_roff.p, n_reads, d_maps.p, d_maps.p + 256, (uint8_t)sigma, ctx->d_cf.p, ctx->d_cr.p);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASB_OK;
+}
+
+int asb_debug_read(asb_ctx* ctx, uint32_t read, int strand, uint8_t* dst, uint32_t cap)
+{
+    if (!ctx || !dst || read >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "bad read id");
+    const uint32_t len = ctx->h_rlen[read];
+    if (cap < len) return fail(ctx, ASB_E_ARG, "buffer too small");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(dst, (strand ? ctx->d_cr.p : ctx->d_cf.p) + ctx->h_roff[read], len, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t i = 0; i < len; ++i) dst[i] = ctx->code_to_ascii[dst[i]];
+    return ASB_OK;
+}
+
+int asb_batch_begin(asb_ctx* ctx, const uint32_t* order, uint32_t n, const uint32_t* hi, const uint32_t* dpass,
+                    const uint32_t* drev, uint32_t table_len, uint32_t rank, uint32_t world)
+{
+    if (!ctx || (n && (!order || !hi)) || !dpass || !drev || world == 0 || rank >= world) return fail(ctx, ASB_E_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->in_batch = false;
+    ctx->n = n; ctx->rank = rank; ctx->world = world; ctx->table_len = table_len;
+    ctx->h_len.resize(n); ctx->h_hi.assign(hi, hi + n);
+    std::vector<uint64_t> pos_off(n);
+    for (uint32_t p = 0; p < n; ++p) {
+        if (order[p] >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "order[%u]=%u is not an uploaded read", p, order[p]);
+        ctx->h_len[p] = ctx->h_rlen[order[p]];
+        pos_off[p] = ctx->h_roff[order[p]];
+        if (p && ctx->h_len[p] < ctx->h_len[p - 1]) return fail(ctx, ASB_E_ARG, "batch is not sorted by length at position %u", p);
+        if (hi[p] < p || hi[p] >= n) return fail(ctx, ASB_E_ARG, "hi[%u]=%u out of range", p, hi[p]);
+        if (ctx->h_len[p] >= table_len) return fail(ctx, ASB_E_ARG, "read length %u >= table_len %u", ctx->h_len[p], table_len);
+    }
+    ctx->h_dpass.assign(dpass, dpass + table_len); ctx->h_drev.assign(drev, drev + table_len);
+    ctx->h_pmax_dpass.resize(table_len); ctx->h_pmax_drev.resize(table_len);
+    uint32_t a = 0, b = 0;
+    for (uint32_t L = 0; L < table_len; ++L) {
+        if (dpass[L] != 0xFFFFFFFFu) a = std::max(a, dpass[L]);
+        b = std::max(b, drev[L]);
+        ctx->h_pmax_dpass[L] = a; ctx->h_pmax_drev[L] = b;
+    }
+    CU(ctx->d_pos_off.ensure(n)); CU(ctx->d_pos_len.ensure(n)); CU(ctx->d_hi.ensure(n));
+    CU(ctx->d_dpass.ensure(table_len)); CU(ctx->d_drev.ensure(table_len));
+    if (n) {
+        CU(cudaMemcpyAsync(ctx->d_pos_off.p, pos_off.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_pos_len.p, ctx->h_len.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_hi.p, hi, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->d_dpass.p, dpass, sizeof(uint32_t) * table_len, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_drev.p, drev, sizeof(uint32_t) * table_len, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));  // pos_off is a local
+    ctx->next_row = 0;
+    ctx->rec_n = 0;
+    ctx->in_batch = true;
+    return ASB_OK;
+}
+
+// window words needed by row p for threshold table `pmax` (conservative): rows c-D..c+E
+static int need_words(const asb_ctx* ctx, uint32_t p, const std::vector<uint32_t>& pmax, int minus)
+{
+    const uint32_t m = ctx->h_len[p], nmax = ctx->h_len[ctx->h_hi[p]];
+    int k = (int)pmax[nmax] - minus;
+    if (k < 0) k = 0;
+    const int dl = (int)(nmax - m);
+    const int D = (k + dl + 1) / 2, E = (k + 1) / 2;
+    return (D + 31) / 32 + (E + 31) / 32 + 1;
+}
+
+int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
+{
+    if (!ctx || !info) return ASB_E_ARG;
+    if (!ctx->in_batch) return fail(ctx, ASB_E_ARG, "asb_batch_step without asb_batch_begin");
+    CU(cudaSetDevice(ctx->device));
+    memset(info, 0, sizeof *info);
+    const uint32_t n = ctx->n;
+    // skip rows without partners
+    uint32_t r0 = ctx->next_row;
+    while (r0 < n && ctx->h_hi[r0] == r0) ++r0;
+    if (n == 0 || r0 >= n) { ctx->next_row = n; ctx->rec_n = 0; return ASB_DONE; }
+    // slab: rows of one window class, at most pair_cap pairs
+    const int cls = class_for(std::min(need_words(ctx, r0, ctx->h_pmax_dpass, 0), (int)((ctx->h_len[r0] + 31) / 32)));
+    uint64_t pairs = 0, groups = 0;
+    uint32_t r1 = r0;
+    int zneed = 0;
+    uint32_t wmax = 1;
+    std::vector<uint32_t> prefix;
+    prefix.push_back(0);
+    while (r1 < n) {
+        const uint64_t cnt = ctx->h_hi[r1] - r1;
+        if (cnt) {
+            const int W = (int)((ctx->h_len[r1] + 31) / 32);
+            const int c2 = class_for(std::min(need_words(ctx, r1, ctx->h_pmax_dpass, 0), W));
+            if (c2 != cls) break;
+            if (r1 > r0 && pairs + cnt > ctx->pair_cap) break;
+            zneed = std::max(zneed, std::min(need_words(ctx, r1, ctx->h_pmax_drev, 1), W));
+            wmax = std::max<uint32_t>(wmax, (uint32_t)W);
+        }
+        pairs += cnt;
+        groups += (cnt + 31) / 32;
+        if (groups > 0xFFFFFFF0ull) return fail(ctx, ASB_E_ARG, "pair_cap too large for 32-bit group indices");
+        prefix.push_back((uint32_t)groups);
+        ++r1;
+    }
+    const int zcls = class_for(zneed);
+    const uint64_t cap = std::max<uint64_t>(pairs, 32);
+    int rc = ensure_lists(ctx, cap);
+    if (rc) return rc;
+    CU(ctx->d_grp.ensure(prefix.size()));
+    CU(cudaMemcpyAsync(ctx->d_grp.p, prefix.data(), sizeof(uint32_t) * prefix.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
+
+    DevBatch B;
+    memset(&B, 0, sizeof B);
+    B.codes_f = ctx->d_cf.p; B.codes_r = ctx->d_cr.p; B.pos_off = ctx->d_pos_off.p; B.pos_len = ctx->d_pos_len.p; B.hi = ctx->d_hi.p;
+    B.dpass = ctx->d_dpass.p; B.drev = ctx->d_drev.p; B.table_len = ctx->table_len; B.n = n; B.sigma = ctx->sigma;
+    B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
+    B.ctr = ctx->d_ctr.p; B.list_cap = ctx->list_cap;
+    B.grp_prefix = ctx->d_grp.p; B.row_begin = r0; B.rows = r1 - r0;
+    B.rank = ctx->rank; B.world = ctx->world;
+    B.n_tasks = groups > ctx->rank ? (uint32_t)((groups - ctx->rank + ctx->world - 1) / ctx->world) : 0;
+    B.screen_cols_num = std::max(1, (int)(ctx->screen_frac * 256.0 + 0.5));
+    B.push_thresh = ctx->push_thresh;
+    const int bt = kClasses[cls];
+    B.Wpad = odd_stride((int)wmax + (bt > 0 ? bt : 0) + 1);
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (B.n_tasks) {
+        screen_fn fn = Fns::screen(cls);
+        const size_t smem = smem_bytes(ctx, B.Wpad);
+        int grid = 0;
+        rc = launch_cfg(ctx, fn, smem, &grid);
+        if (rc) return rc;
+        const uint64_t blocks = ((uint64_t)B.n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        grid = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint64_t>(blocks, 1));
+        fn<<<grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(B);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    rc = read_counters(ctx);
+    if (rc) return rc;
+    const uint64_t nF = ctx->h_ctr[C_F];
+    info->fwd_survivors = nF;
+    uint64_t* keys; uint32_t* vals;
+    // F: full forward pass
+    rc = sort_list(ctx, ctx->d_F.p, nullptr, nF, &keys, nullptr); if (rc) return rc;
+    rc = run_list(ctx, B, M_FWD, cls, keys, nullptr, nF); if (rc) return rc;
+    rc = read_counters(ctx); if (rc) return rc;
+    const uint64_t nR = ctx->h_ctr[C_R];
+    info->rc_survivors = nR;
+    // R: full compl_reverse pass
+    rc = sort_list(ctx, ctx->d_R.p, nullptr, nR, &keys, nullptr); if (rc) return rc;
+    rc = run_list(ctx, B, M_RC, cls, keys, nullptr, nR); if (rc) return rc;
+    rc = read_counters(ctx); if (rc) return rc;
+    const uint64_t nZ = ctx->h_ctr[C_Z];
+    info->zone_checks = nZ;
+    // Z: exact forward decision at drev
+    rc = sort_list(ctx, ctx->d_Z.p, ctx->d_Zv.p, nZ, &keys, &vals); if (rc) return rc;
+    {
+        const int zbt = kClasses[zcls];
+        DevBatch BZ = B;
+        BZ.Wpad = odd_stride((int)wmax + (zbt > 0 ? zbt : 0) + 1);
+        rc = run_list(ctx, BZ, M_ZONE, zcls, keys, vals, nZ); if (rc) return rc;
+    }
+    rc = read_counters(ctx); if (rc) return rc;
+    const uint64_t nO = ctx->h_ctr[C_O];
+    rc = sort_list(ctx, ctx->d_O.p, ctx->d_Ov.p, nO, &ctx->rec_keys, &ctx->rec_vals); if (rc) return rc;
+    ctx->rec_n = nO;
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); info->screen_ms = ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2])); info->total_ms = ms;
+    // pairs owned by this rank: groups dealt cyclically
+    uint64_t my_pairs = 0;
+    if (ctx->world == 1) my_pairs = pairs;
+    else {
+        const uint64_t Wd = ctx->world, rk = ctx->rank;
+        for (uint32_t r = r0; r < r1; ++r) {
+            const uint64_t cnt = ctx->h_hi[r] - r, g0 = prefix[r - r0], g1 = prefix[r - r0 + 1];
+            if (g1 == g0) continue;
+            // groups g in [g0,g1) with g % world == rank
+            const uint64_t first = g0 + ((rk + Wd - g0 % Wd) % Wd);
+            if (first >= g1) continue;
+            const uint64_t mine = (g1 - 1 - first) / Wd + 1;
+            my_pairs += 32 * mine;
+            if ((g1 - 1) % Wd == rk) my_pairs -= 32 * (g1 - g0) - cnt;  // the row's last group is partial
+        }
+    }
+    info->pairs = my_pairs;
+    info->n_records = nO;
+    info->word_updates = ctx->h_ctr[C_WORDS] * 32ull;
+    info->row_begin = r0; info->row_end = r1;
+    ctx->next_row = r1;
+    return ASB_OK;
+}
+
+int asb_batch_records(asb_ctx* ctx, asb_record* dst)
+{
+    if (!ctx) return ASB_E_ARG;
+    if (ctx->rec_n == 0) return ASB_OK;
+    if (!dst) return fail(ctx, ASB_E_ARG, "null destination");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->rec_n;
+    CU(ctx->d_rec.ensure(n));
+    asb_pack_records<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->rec_keys, ctx->rec_vals, n, ctx->d_rec.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dst, ctx->d_rec.p, sizeof(asb_record) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASB_OK;
+}
+
+int asb_distance_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const uint8_t* strand, uint64_t npairs, int mode, int32_t* out_d)
+{
+    if (!ctx || (npairs && (!a || !b || !out_d))) return fail(ctx, ASB_E_ARG, "null argument");
+    if (mode != 0) return fail(ctx, ASB_E_ARG, "only mode 0 (NW) is implemented");
+    if (npairs == 0) return ASB_OK;
+    CU(cudaSetDevice(ctx->device));
+    ctx->in_batch = false;  // reuses the batch position arrays
+    const uint32_t n = ctx->n_reads;
+    // positions == read ids
+    std::vector<uint64_t> keys(npairs);
+    std::vector<uint8_t> st(npairs, 0);
+    uint32_t wmax = 1;
+    for (uint64_t p = 0; p < npairs; ++p) {
+        if (a[p] >= n || b[p] >= n) return fail(ctx, ASB_E_ARG, "pair %llu references a read that was not uploaded", (unsigned long long)p);
+        uint32_t q = a[p], t = b[p];
+        if (ctx->h_rlen[q] > ctx->h_rlen[t]) std::swap(q, t);  // AS:225-230 shorter read is the query
+        keys[p] = ((uint64_t)q << 32) | t;
+        if (strand) st[p] = strand[p] ? 1 : 0;
+        wmax = std::max(wmax, (ctx->h_rlen[q] + 31) / 32);
+    }
+    if (wmax > (uint32_t)kMaxDynWords) return fail(ctx, ASB_E_TOO_LONG, "exact distance supports reads up to %d bases", kMaxDynWords * 32);
+    CU(ctx->d_pos_off.ensure(n)); CU(ctx->d_pos_len.ensure(n));
+    CU(cudaMemcpyAsync(ctx->d_pos_off.p, ctx->h_roff.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_pos_len.p, ctx->h_rlen.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    DevBuf<uint64_t> d_keys; DevBuf<uint8_t> d_st; DevBuf<int32_t> d_out;
+    struct Guard { DevBuf<uint64_t>&a; DevBuf<uint8_t>&b; DevBuf<int32_t>&c; ~Guard(){a.release();b.release();c.release();} } guard{d_keys, d_st, d_out};
+    CU(d_keys.ensure(npairs)); CU(d_st.ensure(npairs)); CU(d_out.ensure(npairs));
+    CU(cudaMemcpyAsync(d_keys.p, keys.data(), sizeof(uint64_t) * npairs, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_st.p, st.data(), npairs, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
+    DevBatch B;
+    memset(&B, 0, sizeof B);
+    B.codes_f = ctx->d_cf.p; B.codes_r = ctx->d_cr.p; B.pos_off = ctx->d_pos_off.p; B.pos_len = ctx->d_pos_len.p;
+    B.n = n; B.sigma = ctx->sigma; B.ctr = ctx->d_ctr.p; B.ex_strand = d_st.p; B.ex_out = d_out.p;
+    B.Wpad = odd_stride((int)wmax + 1);
+    int rc = run_list(ctx, B, M_EXACT, kNumClasses - 1, d_keys.p, nullptr, npairs);
+    if (rc) return rc;
+    rc = read_counters(ctx);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out_d, d_out.p, sizeof(int32_t) * npairs, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASB_OK;
+}
+
+}  // extern "C"

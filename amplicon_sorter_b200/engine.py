@@ -1,0 +1,118 @@
+"""Thin object wrapper over the C ABI (include/asb200.h): one Engine = one GPU context."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import RECORD, EngineError, StepInfo, ptr
+
+
+class Engine:
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = _ffi.load()
+        h = C.c_void_p()
+        rc = self._lib.asb_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h))
+        if rc != 0:
+            raise EngineError(rc, "asb_create failed (no usable CUDA device?)")
+        self._h = h
+        self.device = device
+        self.n_reads = 0
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc < 0:
+            raise EngineError(rc, self._lib.asb_last_error(self._h).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.asb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_param(self, name: str, value: float):
+        self._check(self._lib.asb_set_param(self._h, name.encode(), float(value)))
+
+    # -- reads ---------------------------------------------------------------------------------
+    def upload_reads(self, ascii_buf: np.ndarray, offs: np.ndarray):
+        ascii_buf = np.ascontiguousarray(ascii_buf, dtype=np.uint8)
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = offs.shape[0] - 1
+        self._check(self._lib.asb_upload_reads(self._h, ptr(ascii_buf, C.c_uint8), ptr(offs, C.c_uint64), n))
+        self.n_reads = n
+        self._lens = (offs[1:] - offs[:-1]).astype(np.uint32)
+
+    def debug_read(self, r: int, strand: int = 0) -> bytes:
+        out = np.empty(int(self._lens[r]), dtype=np.uint8)
+        self._check(self._lib.asb_debug_read(self._h, r, strand, ptr(out, C.c_uint8), out.shape[0]))
+        return out.tobytes()
+
+    # -- all-pairs batch -------------------------------------------------------------------------
+    def batch_begin(self, order, hi, dpass, drev, rank=0, world=1):
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        hi = np.ascontiguousarray(hi, dtype=np.uint32)
+        dpass = np.ascontiguousarray(dpass, dtype=np.uint32)
+        drev = np.ascontiguousarray(drev, dtype=np.uint32)
+        assert dpass.shape == drev.shape
+        self._keep = (order, hi, dpass, drev)
+        self._check(self._lib.asb_batch_begin(self._h, ptr(order, C.c_uint32), order.shape[0], ptr(hi, C.c_uint32),
+                                              ptr(dpass, C.c_uint32), ptr(drev, C.c_uint32), dpass.shape[0], rank, world))
+
+    def batch_step(self):
+        """Run the next slab.  Returns a StepInfo dict, or None when the batch is exhausted."""
+        info = StepInfo()
+        rc = self._check(self._lib.asb_batch_step(self._h, C.byref(info)))
+        if rc == _ffi.ASB_DONE:
+            return None
+        return info.as_dict()
+
+    def batch_records(self, n_records: int) -> np.ndarray:
+        out = np.empty(n_records, dtype=RECORD)
+        if n_records:
+            self._check(self._lib.asb_batch_records(self._h, out.ctypes.data))
+        return out
+
+    def compare_batch(self, order, hi, dpass, drev, rank=0, world=1, fetch=True):
+        """All steps of one batch.  Returns (records sorted by (i_pos, j_pos), totals dict)."""
+        self.batch_begin(order, hi, dpass, drev, rank, world)
+        recs = []
+        tot = {"pairs": 0, "n_records": 0, "fwd_survivors": 0, "rc_survivors": 0, "zone_checks": 0,
+               "word_updates": 0, "screen_ms": 0.0, "total_ms": 0.0, "steps": 0}
+        while True:
+            info = self.batch_step()
+            if info is None:
+                break
+            for k in tot:
+                if k in info:
+                    tot[k] += info[k]
+            tot["steps"] += 1
+            if fetch and info["n_records"]:
+                recs.append(self.batch_records(info["n_records"]))
+        out = np.concatenate(recs) if recs else np.empty(0, dtype=RECORD)
+        return out, tot
+
+    # -- distance() on explicit pairs --------------------------------------------------------------
+    def distance_pairs(self, a, b, strand=None) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        out = np.empty(a.shape[0], dtype=np.int32)
+        sp = None
+        if strand is not None:
+            strand = np.ascontiguousarray(strand, dtype=np.uint8)
+            sp = ptr(strand, C.c_uint8)
+        self._check(self._lib.asb_distance_pairs(self._h, ptr(a, C.c_uint32), ptr(b, C.c_uint32), sp, a.shape[0], 0,
+                                                 ptr(out, C.c_int32)))
+        return out

@@ -1,0 +1,177 @@
+"""Host-side mirror of the reference's all-pairs stage: same names, arguments and side effects.
+
+``process_list(comparelist2, tempfile)`` replaces amplicon_sorter.py:647-774 (queuer / feeder /
+consumer threads, forked ``similarity`` workers :776-807) with one GPU engine call per batch.  The
+Python host keeps what the reference keeps in Python: the stable length sort (:669), the window test
+``len_i*1.05 < len_j`` (:679) in the reference's float arithmetic, the text formatting of
+``iden = round(1 - d/len, 3)`` (:233) and the tempfile protocol.  Everything O(N^2) happens on the GPU.
+"""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+from . import thresholds
+from .engine import Engine
+
+
+class NoReadsToCompare(Exception):
+    """amplicon_sorter.py:702-706 + :768-772: zero comparable pairs -> skip this input file."""
+
+
+def batch_geometry(lengths_sorted: np.ndarray):
+    """hi[p] = last position j kept by the window test of amplicon_sorter.py:679 for row p.
+
+    The batch is sorted by length, so the kept partners of row p are the contiguous positions
+    p+1 .. hi[p].  The test is `len_i*1.05 < len_j` -> skip, evaluated in float64 exactly as Python
+    does (int*float -> float; int < 2**53 compares exactly).
+    """
+    L = np.asarray(lengths_sorted, dtype=np.int64)
+    lim = L.astype(np.float64) * 1.05
+    # last j with not (lim_i < L_j)  <=>  L_j <= lim_i
+    hi = np.searchsorted(L.astype(np.float64), lim, side="right").astype(np.int64) - 1
+    hi = np.maximum(hi, np.arange(L.shape[0]))
+    return hi.astype(np.uint32)
+
+
+def _iden_strings(lens_long: np.ndarray, d: np.ndarray):
+    """str(round(1 - d/L, 3)) per record, computed with Python's own float/round/str on the unique
+    (L, d) combinations only."""
+    key = lens_long.astype(np.uint64) << np.uint64(32) | d.astype(np.uint64)
+    uniq, inv = np.unique(key, return_inverse=True)
+    table = np.empty(uniq.shape[0], dtype=object)
+    for t, k in enumerate(uniq.tolist()):
+        L, dd = k >> 32, k & 0xFFFFFFFF
+        table[t] = str(round(1 - dd / L, 3))
+    return table[inv]
+
+
+def format_records(records: np.ndarray, idx_sorted: np.ndarray, lens_sorted: np.ndarray) -> str:
+    """Records -> the lines of amplicon_sorter.py:792-798: 'idxA:idxB:iden' or '...:reverse'."""
+    if records.shape[0] == 0:
+        return ""
+    a = idx_sorted[records["i_pos"]]
+    b = idx_sorted[records["j_pos"]]
+    iden = _iden_strings(lens_sorted[records["j_pos"]], records["d"])
+    rev = records["reverse"].astype(bool)
+    parts = []
+    for x, y, s, r in zip(a.tolist(), b.tolist(), iden.tolist(), rev.tolist()):
+        parts.append(f"{x}:{y}:{s}:reverse\n" if r else f"{x}:{y}:{s}\n")
+    return "".join(parts)
+
+
+class AllPairs:
+    """State shared by the batches of one input file: one engine, reads uploaded once."""
+
+    def __init__(self, engine: Engine | None = None, device: int = 0):
+        self.engine = engine or Engine(device)
+        self.stats = {"pairs": 0, "records": 0, "fwd_survivors": 0, "rc_survivors": 0, "zone_checks": 0,
+                      "word_updates": 0, "gpu_ms": 0.0, "screen_ms": 0.0}
+
+    def upload(self, seqs: list[str]):
+        lens = np.fromiter((len(s) for s in seqs), dtype=np.uint64, count=len(seqs))
+        offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum(lens, out=offs[1:])
+        buf = np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8)
+        self.engine.upload_reads(buf, offs)
+        self.lens = lens.astype(np.int64)
+
+    def compare(self, read_ids: np.ndarray, similar_genes: float, rank=0, world=1):
+        """One batch (read ids in the batch's CURRENT list order).  Returns (order, records, tl)."""
+        read_ids = np.asarray(read_ids, dtype=np.int64)
+        lens = self.lens[read_ids]
+        perm = np.argsort(lens, kind="stable")  # d.sort(key=lambda x: len(x[1]))  :669
+        order = read_ids[perm].astype(np.uint32)
+        lens_sorted = lens[perm]
+        hi = batch_geometry(lens_sorted)
+        tl = int((hi.astype(np.int64) - np.arange(hi.shape[0])).sum())
+        if tl == 0:
+            return perm, order, lens_sorted, np.empty(0, dtype=self._rec_dtype()), 0
+        max_len = int(lens_sorted[-1])
+        dpass, drev = thresholds.tables(similar_genes / 100, max_len + 1)  # similarg :783
+        recs, tot = self.engine.compare_batch(order, hi, dpass, drev, rank, world)
+        self.stats["pairs"] += tot["pairs"]
+        self.stats["records"] += tot["n_records"]
+        for k in ("fwd_survivors", "rc_survivors", "zone_checks", "word_updates", "screen_ms"):
+            self.stats[k] += tot[k]
+        self.stats["gpu_ms"] += tot["total_ms"]
+        return perm, order, lens_sorted, recs, tl
+
+    @staticmethod
+    def _rec_dtype():
+        from ._ffi import RECORD
+        return RECORD
+
+
+def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: dict | None = None):
+    """Drop-in for ``process_list(self, tempfile)`` (amplicon_sorter.py:647).
+
+    self     : comparelist2 -- list of batches of [id, SEQ, tag, idx] records (:568-622)
+    tempfile : os.path.join(outputfolder, '<stem>_compare.tmp') as passed at :2041
+    args     : the reference's argparse namespace (uses .outputfolder, .similar_genes)
+
+    Side effects kept: (1) every batch list is left sorted by length in place (:669); (2) the
+    tempfile holds one line per passing pair in the -np 1 order (batch, i, j) and exists (possibly
+    empty) whenever at least one pair was compared (:802-807 opens it in append mode per chunk);
+    (3) zero comparable pairs -> 'No reads to compare, exiting...' is appended to results.txt and an
+    Exception skips the file (:702-706, :768-772); (4) stale *.todo spool files are removed (:655-660).
+    """
+    outputfolder = args.outputfolder
+    for x in glob.glob(os.path.join(outputfolder, "*.todo")):
+        try:
+            os.remove(x)
+        except FileNotFoundError:
+            pass
+    out_path = os.path.join(outputfolder, tempfile)  # :779-780 joins again; absolute paths win
+    try:
+        os.remove(out_path)
+    except FileNotFoundError:
+        pass
+
+    # distinct records of all batches, keyed by their idx field (:560-561); -ra batches overlap
+    idx_to_rid: dict = {}
+    seqs: list = []
+    batch_rids = []
+    for d in self:
+        rids = np.empty(len(d), dtype=np.int64)
+        for t, rec in enumerate(d):
+            key = rec[3]
+            rid = idx_to_rid.get(key)
+            if rid is None:
+                rid = len(seqs)
+                idx_to_rid[key] = rid
+                seqs.append(rec[1])
+            rids[t] = rid
+        batch_rids.append(rids)
+    rid_to_idx = np.empty(len(seqs), dtype=np.int64)
+    for key, rid in idx_to_rid.items():
+        rid_to_idx[rid] = key
+
+    ap = AllPairs(engine)
+    ap.upload(seqs)
+    tl_total = 0
+    wrote = False
+    for d, rids in zip(self, batch_rids):
+        if len(d) == 0:
+            continue
+        perm, order, lens_sorted, recs, tl = ap.compare(rids, args.similar_genes)
+        d[:] = [d[i] for i in perm.tolist()]  # side effect (1): batch left length-sorted in place
+        tl_total += tl
+        if tl:
+            text = format_records(recs, rid_to_idx[order.astype(np.int64)], lens_sorted)
+            with open(out_path, "a") as f:  # :803
+                f.write(text)
+            wrote = True
+    if stats_out is not None:
+        stats_out.update(ap.stats)
+        stats_out["tl"] = tl_total
+    if engine is None:
+        ap.engine.close()
+    if tl_total == 0:
+        print("No reads to compare, exiting...")
+        with open(os.path.join(outputfolder, "results.txt"), "a") as rf:
+            rf.write("No reads to compare, exiting...")
+        raise NoReadsToCompare()
+    return None

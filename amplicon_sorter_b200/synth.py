@@ -1,0 +1,150 @@
+"""Synthetic ONT-like amplicon reads for the five BASELINE.json configs.
+
+Error model ("ONT-like"): per base 3 % substitution, 1.5 % insertion, 1.5 % deletion, indel rates
+doubled inside homopolymer runs >= 3; strand chosen 50/50; ids ``r{n}``; FASTQ quality constant 'I'.
+Everything is seeded (numpy PCG64), so a config name + seed fully determines the reads.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.array([3, 2, 1, 0], dtype=np.uint8)  # A<->T, C<->G on 0..3 codes
+
+
+def random_template(rng, length: int) -> np.ndarray:
+    return rng.integers(0, 4, size=length, dtype=np.uint8)
+
+
+def diverge(rng, tmpl: np.ndarray, frac: float) -> np.ndarray:
+    """A relative of `tmpl` at ~`frac` divergence (substitutions 80 %, indels 20 %)."""
+    return mutate(rng, tmpl, sub=0.8 * frac, ins=0.1 * frac, dele=0.1 * frac, homopolymer_boost=1.0)
+
+
+def mutate(rng, tmpl: np.ndarray, sub=0.03, ins=0.015, dele=0.015, homopolymer_boost=2.0) -> np.ndarray:
+    L = tmpl.shape[0]
+    if L == 0:
+        return tmpl.copy()
+    # homopolymer runs >= 3
+    change = np.empty(L, dtype=bool)
+    change[0] = True
+    np.not_equal(tmpl[1:], tmpl[:-1], out=change[1:])
+    run_id = np.cumsum(change) - 1
+    run_len = np.bincount(run_id)[run_id]
+    boost = np.where(run_len >= 3, homopolymer_boost, 1.0)
+    u = rng.random((3, L))
+    deleted = u[0] < dele * boost
+    inserted = u[1] < ins * boost
+    subbed = u[2] < sub
+    base = tmpl.copy()
+    nsub = int(subbed.sum())
+    if nsub:
+        base[subbed] = (base[subbed] + rng.integers(1, 4, size=nsub, dtype=np.uint8)) & 3
+    counts = (~deleted).astype(np.int64) + inserted.astype(np.int64)
+    out = np.repeat(base, counts)
+    ends = np.cumsum(counts) - 1
+    ins_pos = ends[inserted]
+    if ins_pos.size:
+        out[ins_pos] = rng.integers(0, 4, size=ins_pos.size, dtype=np.uint8)
+    return out
+
+
+def revcomp_codes(x: np.ndarray) -> np.ndarray:
+    return _COMP[x[::-1]]
+
+
+def _emit(rng, templates, counts, shuffle=True, n_frac=0.0, err=None):
+    """reads (list of bytes) from templates with per-template counts; optional fraction of reads
+    carrying a few 'N's."""
+    err = err or {}
+    reads = []
+    labels = []
+    for t, (tmpl, c) in enumerate(zip(templates, counts)):
+        for _ in range(int(c)):
+            r = mutate(rng, tmpl, **err)
+            if rng.random() < 0.5:
+                r = revcomp_codes(r)
+            s = _ACGT[r]
+            if n_frac and rng.random() < n_frac and s.size:
+                s = s.copy()
+                k = int(rng.integers(1, 4))
+                s[rng.integers(0, s.size, size=k)] = ord("N")
+            reads.append(s.tobytes())
+            labels.append(t)
+    if shuffle:
+        perm = rng.permutation(len(reads))
+        reads = [reads[i] for i in perm]
+        labels = [labels[i] for i in perm]
+    return reads, labels
+
+
+def make_config(cfg: int, scale: float = 1.0, seed: int | None = None):
+    """Return (reads, labels, cli_args) for BASELINE config `cfg` (1..5).
+
+    `scale` shrinks the read count (same template structure) for parity tests and bounded samples.
+    cli_args is the reference command line for that config, without -i/-o.
+    """
+    seeds = {1: 101, 2: 102, 3: 103, 4: 104, 5: 105}
+    rng = np.random.default_rng(seeds[cfg] if seed is None else seed)
+    if cfg == 1:
+        n = max(5, int(round(1000 * scale)))
+        T = [random_template(rng, 700) for _ in range(5)]
+        counts = _split(n, 5)
+        reads, labels = _emit(rng, T, counts)
+        return reads, labels, ["-np", "1"]
+    if cfg == 2:
+        n = max(12, int(round(10000 * scale)))
+        T = []
+        for glen in (1800, 700, 1000):
+            anc = random_template(rng, glen)
+            for _ in range(4):
+                T.append(diverge(rng, anc, float(rng.uniform(0.04, 0.12))))
+        reads, labels = _emit(rng, T, _split(n, len(T)))
+        return reads, labels, ["-a", "-maxr", str(n)]
+    if cfg == 3:
+        n = max(50, int(round(10000 * scale)))
+        anc = random_template(rng, 700)
+        T = [diverge(rng, anc, float(rng.uniform(0.03, 0.15))) for _ in range(50)]
+        w = np.exp(rng.uniform(np.log(1.0), np.log(50.0), size=50))
+        counts = np.maximum(1, np.floor(w / w.sum() * n)).astype(int)
+        counts[0] += n - counts.sum() if n > counts.sum() else 0
+        reads, labels = _emit(rng, T, counts)
+        return reads, labels, ["-ra", "-maxr", str(2 * len(reads))]
+    if cfg == 4:
+        n = max(20, int(round(50000 * scale)))
+        T = []
+        for _ in range(10):
+            full = random_template(rng, 1000)
+            T.append(full)
+            T.append(full[65:935].copy())  # nested amplicon, 870 bp
+        reads, labels = _emit(rng, T, _split(n, len(T)))
+        return reads, labels, ["-a", "-maxr", str(n), "-ldc", "20", "-sc", "96"]
+    if cfg == 5:
+        n = max(200, int(round(100000 * scale)))
+        T = [random_template(rng, 1000) for _ in range(200)]
+        reads, labels = _emit(rng, T, _split(n, 200), n_frac=0.01)
+        return reads, labels, ["-a", "-maxr", str(n)]
+    raise ValueError(f"unknown config {cfg}")
+
+
+def _split(n, k):
+    base = n // k
+    c = [base] * k
+    for i in range(n - base * k):
+        c[i] += 1
+    return c
+
+
+def write_fastq(path, reads, prefix="r"):
+    with open(path, "wb") as f:
+        for i, s in enumerate(reads):
+            f.write(b"@" + prefix.encode() + str(i).encode() + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n")
+
+
+def pack_reads(reads):
+    """list[bytes] -> (uint8 concatenation, uint64 offsets[n+1]) -- the C-ABI read layout."""
+    lens = np.fromiter((len(r) for r in reads), dtype=np.uint64, count=len(reads))
+    offs = np.zeros(len(reads) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    buf = np.frombuffer(b"".join(reads), dtype=np.uint8).copy() if len(reads) else np.zeros(0, np.uint8)
+    return buf, offs

@@ -1,0 +1,99 @@
+/*
+ * asb200.h -- C ABI of the B200 all-pairs read-similarity engine (libasb200.so).
+ *
+ * This is the drop-in boundary for ONE path of avierstr/amplicon_sorter: the all-pairs stage
+ * `process_list` (amplicon_sorter.py:647-774) with its worker `similarity` (:776-807), scorer
+ * `distance` (:224-234, i.e. edlib.align(task='distance', mode='NW') at :231) and
+ * `compl_reverse` (:236-241).  The reference has no FFI; the binding a maintainer would add is a
+ * ctypes stub.  Plain pointers and sizes only; no C++/torch types; no
+ * exceptions cross the boundary -- every entry point returns an asb_status.
+ *
+ * Threading: a context owns one CUDA device + stream and is NOT re-entrant.
+ * There is no CPU fallback anywhere behind this header.
+ */
+#ifndef ASB200_H
+#define ASB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct asb_ctx asb_ctx;
+
+typedef enum {
+    ASB_OK = 0,
+    ASB_DONE = 1,          /* asb_batch_step: no step left */
+    ASB_E_CUDA = -1,       /* a CUDA runtime call failed (see asb_last_error) */
+    ASB_E_ARG = -2,        /* invalid argument / call order */
+    ASB_E_NOMEM = -3,      /* host or device allocation failed */
+    ASB_E_TOO_LONG = -4,   /* a read needs a wider band than the engine supports */
+    ASB_E_INTERNAL = -5    /* device-side invariant violated (a bug) */
+} asb_status;
+
+/* One emitted line of <stem>_compare.tmp (amplicon_sorter.py:792-798) in integer form.  The
+ * host formats `iden` itself with the reference's expression round(1 - d/len_long, 3). */
+typedef struct {
+    uint32_t i_pos;   /* position of the shorter read in the length-sorted batch (:669) */
+    uint32_t j_pos;   /* position of the longer read, i_pos < j_pos */
+    uint32_t d;       /* edit distance behind the emitted iden (forward, or vs compl_reverse) */
+    uint32_t reverse; /* 1 = the ':reverse' branch (:795-798) */
+} asb_record;
+
+typedef struct {
+    uint64_t pairs;          /* length-compatible pairs decided in this step = reference's tl (:684) */
+    uint64_t n_records;      /* records emitted by this step (sorted by i_pos, j_pos) */
+    uint64_t fwd_survivors;  /* pairs the screen could not reject on the forward strand */
+    uint64_t rc_survivors;   /* pairs the screen could not reject on the reverse strand */
+    uint64_t zone_checks;    /* pairs that needed the exact "forward iden < 0.5" decision (:794) */
+    uint64_t word_updates;   /* 32-row Myers word-updates executed by all kernels of the step */
+    uint32_t row_begin, row_end; /* rows [row_begin,row_end) of the sorted batch covered */
+    float screen_ms;         /* device time of the dominant kernel (asb_screen) in this step */
+    float total_ms;          /* device time of the whole step */
+} asb_step_info;
+
+/* Replaces nothing in the reference (it has no device): create/destroy an engine on `device`.
+ * `stream` is a cudaStream_t to enqueue on (e.g. torch's current stream) or NULL for a private one. */
+int asb_create(int device, void *stream, asb_ctx **out);
+void asb_destroy(asb_ctx *ctx);
+const char *asb_last_error(const asb_ctx *ctx);
+/* Tuning knobs: "pair_cap", "screen_frac", "push_thresh", "count_words". */
+int asb_set_param(asb_ctx *ctx, const char *name, double value);
+
+/* Replaces the per-record `str(record.seq).upper()` payload (:551) + per-pair compl_reverse (:795):
+ * uploads upper-case reads (read r = ascii[offs[r] .. offs[r+1])), builds the byte alphabet of
+ * the data (edlib semantics: every distinct character is its own symbol) and the forward and
+ * compl_reverse symbol codes in HBM.  Buffers are caller-owned and copied during the call. */
+int asb_upload_reads(asb_ctx *ctx, const uint8_t *ascii, const uint64_t *offs, uint32_t n_reads);
+
+/* Replaces process_list.queuer (:662-715) for one batch.  order[n] = read ids in the stable
+ * length-sorted order of :669; hi[p] = last position j kept by the window test :679 for row p
+ * (hi[p] >= p; hi[p] == p means no partner); dpass/drev[L] = integer cut-offs for a longer read
+ * of length L (see thresholds.py): pass iff d <= dpass[L]; retry on compl_reverse iff d >= drev[L].
+ * (rank, world) shards the 32-target groups of every row cyclically; a single GPU is (0, 1). */
+int asb_batch_begin(asb_ctx *ctx, const uint32_t *order, uint32_t n, const uint32_t *hi,
+                    const uint32_t *dpass, const uint32_t *drev, uint32_t table_len,
+                    uint32_t rank, uint32_t world);
+/* Replaces similarity (:776-807) for the next slab of rows.  ASB_OK: a step ran, *info filled;
+ * ASB_DONE: batch exhausted. */
+int asb_batch_step(asb_ctx *ctx, asb_step_info *info);
+/* Copies the records of the last step (info.n_records of them) to host memory. */
+int asb_batch_records(asb_ctx *ctx, asb_record *dst);
+
+/* Replaces distance(X1, X2, mode) (:224-234) on an explicit pair list of uploaded read ids:
+ * out_d[p] = exact edit distance, NW (mode 0) between a[p] and b[p] (shorter one is the query);
+ * strand 1 compares against compl_reverse of the longer read. */
+int asb_distance_pairs(asb_ctx *ctx, const uint32_t *a, const uint32_t *b, const uint8_t *strand,
+                       uint64_t npairs, int mode, int32_t *out_d);
+
+/* Introspection for tests: symbol codes of read r (forward or compl_reverse) as the device holds
+ * them, translated back to ASCII. */
+int asb_debug_read(asb_ctx *ctx, uint32_t read, int strand, uint8_t *dst, uint32_t cap);
+
+int asb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASB200_H */

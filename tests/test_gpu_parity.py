@@ -1,0 +1,189 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bar: bit-exact.  Edit distances, pass/fail decisions, the reverse flag and the record order are
+integers and must match the oracle exactly."""
+import numpy as np
+import pytest
+
+from amplicon_sorter_b200 import synth, thresholds
+from oracle import oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def test_encode_roundtrip_and_compl_reverse(engine):
+    reads = [b"ACGT", b"A", b"AACGTNRYKMSWBDHV-X", b"N" * 33, b"ACGT" * 300 + b"ACG"]
+    buf, offs = synth.pack_reads(reads)
+    engine.upload_reads(buf, offs)
+    for r, s in enumerate(reads):
+        assert engine.debug_read(r, 0) == s
+        assert engine.debug_read(r, 1) == oracle.compl_reverse(s)
+
+
+def test_exact_distance_known_and_boundaries(engine):
+    rng = np.random.default_rng(21)
+    al = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = [b"A", b"C", b"ACGT", b"AGGT", b"ACGGT", b"AGT", b"AAAA", b"TTTT", b"KITTEN", b"SITTING", b"ACGTN", b"ACGTA"]
+    for m in (31, 32, 33, 63, 64, 65, 95, 96, 97, 1023, 1024, 1025, 1500):
+        a = al[rng.integers(0, 4, m)]
+        reads += [a.tobytes(), a[1:].tobytes(), synth.mutate(rng, a % 4).astype(np.uint8).tobytes() if False else al[synth.mutate(rng, (a == ord("C")) * 1 + (a == ord("G")) * 2 + (a == ord("T")) * 3)].tobytes(),
+                  al[rng.integers(0, 4, m)].tobytes()]
+    buf, offs = synth.pack_reads(reads)
+    engine.upload_reads(buf, offs)
+    n = len(reads)
+    a = rng.integers(0, n, 600).astype(np.uint32)
+    b = rng.integers(0, n, 600).astype(np.uint32)
+    a[:12], b[:12] = np.arange(12), np.roll(np.arange(12), 1)
+    got = engine.distance_pairs(a, b)
+    want = oracle.distance_pairs(buf, offs, a, b, algo="dp")
+    assert np.array_equal(got, want)
+    # reverse strand: distance to compl_reverse of the longer read
+    strand = np.ones(a.shape[0], dtype=np.uint8)
+    got_r = engine.distance_pairs(a, b, strand)
+    for p in range(0, 600, 7):
+        x, y = reads[a[p]], reads[b[p]]
+        if len(x) > len(y):
+            x, y = y, x
+        assert got_r[p] == oracle.nw(x, oracle.compl_reverse(y), "myers")
+
+
+@pytest.mark.parametrize("cfg,scale", [(1, 0.3), (2, 0.06), (3, 0.05), (4, 0.016), (5, 0.012)])
+def test_batch_parity_on_baseline_configs(engine, cfg, scale):
+    reads, _, _ = synth.make_config(cfg, scale=scale)
+    got, tot = util.gpu_batch(engine, reads)
+    want, st = util.oracle_batch(reads)
+    assert tot["pairs"] == st["pairs"]
+    util.assert_same_records(got, want)
+    assert st["records"] > 0
+
+
+@pytest.mark.parametrize("sg", [50.0, 65.0, 80.0, 90.0, 97.0, 100.0])
+def test_batch_parity_thresholds(engine, sg):
+    rng = np.random.default_rng(int(sg))
+    reads = util.random_reads(rng, 260, 300, 420, families=6, err=0.10)
+    reads += util.random_reads(rng, 40, 300, 420)                        # unrelated
+    reads += [reads[0], reads[0], reads[1][:-1], oracle.compl_reverse(reads[2])]  # identical / near-identical / exact RC
+    got, tot = util.gpu_batch(engine, reads, sg)
+    want, st = util.oracle_batch(reads, sg)
+    assert tot["pairs"] == st["pairs"]
+    util.assert_same_records(got, want)
+
+
+def test_batch_parity_non_acgt_and_ragged_lengths(engine):
+    rng = np.random.default_rng(33)
+    reads = util.random_reads(rng, 120, 1, 70, alphabet=b"ACGTN", families=0)
+    reads += util.random_reads(rng, 80, 30, 40, families=2, err=0.05)
+    reads += [b"A", b"A", b"N", b"ACGTRYKMSWN" * 3, oracle.compl_reverse(b"ACGTRYKMSWN" * 3), b"ACGTRYKMSWN" * 3]
+    got, tot = util.gpu_batch(engine, reads, 70.0)
+    want, st = util.oracle_batch(reads, 70.0)
+    assert tot["pairs"] == st["pairs"]
+    util.assert_same_records(got, want)
+
+
+def test_long_reads_use_wide_and_dynamic_windows(engine):
+    rng = np.random.default_rng(34)
+    reads = util.random_reads(rng, 24, 2400, 2500, families=2, err=0.06)     # 18S-like
+    reads += util.random_reads(rng, 10, 7000, 7200, families=1, err=0.06)    # needs the dynamic window at sg=50
+    for sg in (80.0, 50.0):
+        got, tot = util.gpu_batch(engine, reads, sg)
+        want, st = util.oracle_batch(reads, sg)
+        assert tot["pairs"] == st["pairs"]
+        util.assert_same_records(got, want)
+
+
+def test_screen_parameters_do_not_change_results(engine):
+    """Early-termination / survivor routing is an optimisation: any setting gives identical records."""
+    reads, _, _ = synth.make_config(1, scale=0.25)
+    want, _ = util.oracle_batch(reads)
+    for frac, push in ((0.2, 0), (0.4, 31), (1.0, 0), (0.62, 3), (0.05, 8)):
+        got, _ = util.gpu_batch(engine, reads, screen_frac=frac, push_thresh=push)
+        util.assert_same_records(got, want)
+    engine.set_param("screen_frac", 0.62)
+    engine.set_param("push_thresh", 3)
+
+
+def test_small_pair_cap_multi_step_and_sharding(engine):
+    reads, _, _ = synth.make_config(2, scale=0.04)
+    want, st = util.oracle_batch(reads)
+    got, tot = util.gpu_batch(engine, reads, pair_cap=2048)
+    assert tot["steps"] > 3 and tot["pairs"] == st["pairs"]
+    util.assert_same_records(got, want)
+    for world in (2, 3, 8):
+        got, tot = util.gpu_batch(engine, reads, world=world, pair_cap=5000)
+        assert tot["pairs"] == st["pairs"]  # the shards partition the pair set
+        util.assert_same_records(got, want)
+    engine.set_param("pair_cap", float(1 << 26))
+
+
+def _edge_pairs(rng, L, sg):
+    """Engineer reads whose forward/reverse distances sit exactly on the integer cut-offs."""
+    dp, dr = thresholds.tables(sg / 100, L + 64)
+    al = np.frombuffer(b"ACGT", dtype=np.uint8)
+    q = al[rng.integers(0, 4, L)]
+    reads = [q.tobytes()]
+    want_fwd = [int(dp[L]) - 1, int(dp[L]), int(dp[L]) + 1, int(dp[L]) + 2]
+    # forward edge: substitutions at distinct spaced positions, adjusted by the oracle
+    for target in want_fwd:
+        t = q.copy()
+        pos = rng.permutation(L)
+        k = 0
+        while oracle.nw(q.tobytes(), t.tobytes(), "myers") < target:
+            t[pos[k]] = al[(np.where(al == t[pos[k]])[0][0] + 1 + rng.integers(0, 3)) % 4]
+            k += 1
+        reads.append(t.tobytes())
+    # zone edge: T with d(q, rc(T)) small but d(q, T) exactly drev-1 / drev (needs a near-palindromic q)
+    return reads, dp, dr
+
+
+def test_threshold_edges_forward(engine):
+    rng = np.random.default_rng(35)
+    for L, sg in ((700, 80.0), (1024, 80.0), (333, 93.0)):
+        reads, dp, dr = _edge_pairs(rng, L, sg)
+        got, _ = util.gpu_batch(engine, reads, sg)
+        want, _ = util.oracle_batch(reads, sg)
+        util.assert_same_records(got, want)
+        row0 = want[want["i_pos"] == 0]
+        assert dp[L] in row0["d"].tolist() and dp[L] + 1 not in row0["d"].tolist()
+
+
+def test_dead_zone_edges(engine):
+    """Pairs whose compl_reverse passes, with the forward distance walked across drev-1 / drev:
+    the record must appear iff d_fwd >= drev (the reference's `elif iden < 0.5`, AS:794)."""
+    rng = np.random.default_rng(36)
+    al = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = {65: 84, 84: 65, 67: 71, 71: 67}
+    L, sg = 400, 80.0
+    dp, dr = thresholds.tables(sg / 100, L + 8)
+    found = {int(dr[L]) - 2: 0, int(dr[L]) - 1: 0, int(dr[L]): 0, int(dr[L]) + 1: 0}
+    reads = []
+    for attempt in range(60):
+        # q = Y + M + rc(Y): rc(q) = Y + rc(M) + rc(Y), so d(q, rc(q)) = d(M, rc(M)), tunable via |M|
+        mid = int(rng.integers(int(0.90 * L), L - 2)) & ~1
+        y = al[rng.integers(0, 4, (L - mid) // 2)]
+        M = al[rng.integers(0, 4, mid)]
+        rcy = np.array([comp[c] for c in y[::-1]], dtype=np.uint8)
+        q = np.concatenate([y, M, rcy])
+        t = np.frombuffer(oracle.compl_reverse(q.tobytes()), dtype=np.uint8).copy()  # rc(t) == q: reverse passes with d=0
+        d = oracle.nw(q.tobytes(), t.tobytes(), "myers")
+        # walk single substitutions in the middle until d_fwd hits a wanted value
+        for _ in range(400):
+            if d in found and found[d] < 3:
+                found[d] += 1
+                reads += [q.tobytes(), t.tobytes()]
+                break
+            p = int(rng.integers(len(y), len(y) + mid))
+            t2 = t.copy()
+            t2[p] = al[rng.integers(0, 4)]
+            d2 = oracle.nw(q.tobytes(), t2.tobytes(), "myers")
+            goal = min(found, key=lambda v: (found[v] >= 3, abs(v - d)))
+            if abs(d2 - goal) <= abs(d - goal):
+                t, d = t2, d2
+        if all(v >= 2 for v in found.values()):
+            break
+    assert all(v >= 1 for v in found.values()), found
+    got, tot = util.gpu_batch(engine, reads, sg)
+    want, st = util.oracle_batch(reads, sg)
+    util.assert_same_records(got, want)
+    assert tot["zone_checks"] >= sum(found.values())
+    assert (want["reverse"] == 1).sum() >= 2  # some dead-zone pairs emit, some are suppressed
