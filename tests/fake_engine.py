@@ -1,0 +1,61 @@
+"""The CPU oracle behind the Engine interface -- lets CPU tests drive the product's HOST code
+(host.process_list, launcher) end to end without a GPU.  Test infrastructure, never shipped."""
+import numpy as np
+
+from amplicon_sorter_b200._ffi import RECORD
+from oracle import oracle
+
+
+class OracleEngine:
+    def __init__(self):
+        self.closed = False
+
+    def upload_reads(self, buf, offs):
+        self.buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self.offs = np.ascontiguousarray(offs, dtype=np.uint64)
+
+    def set_param(self, *a):
+        pass
+
+    def compare_batch(self, order, hi, dpass, drev, rank=0, world=1, fetch=True):
+        """Same contract as Engine.compare_batch, decisions taken with the integer tables so the
+        host-built thresholds are what is being exercised."""
+        order = np.asarray(order, dtype=np.uint32)
+        n = order.shape[0]
+        lens = (self.offs[1:] - self.offs[:-1]).astype(np.int64)[order]
+        rows = []
+        pairs = 0
+        g = 0
+        for i in range(n):
+            cnt = int(hi[i]) - i
+            if cnt <= 0:
+                continue
+            js = np.arange(i + 1, int(hi[i]) + 1)
+            grp = g + (js - (i + 1)) // 32
+            g += (cnt + 31) // 32
+            js = js[grp % world == rank]
+            if js.size == 0:
+                continue
+            pairs += js.size
+            a = np.full(js.size, order[i], dtype=np.uint32)
+            b = order[js]
+            d = oracle.distance_pairs(self.buf, self.offs, a, b)
+            L = lens[js]
+            fwd = d <= dpass[L].astype(np.int64)
+            need = (~fwd) & (d >= drev[L].astype(np.int64))
+            for t in np.nonzero(fwd)[0]:
+                rows.append((i, int(js[t]), int(d[t]), 0))
+            for t in np.nonzero(need)[0]:
+                x = self.buf[self.offs[order[i]]:self.offs[order[i] + 1]].tobytes()
+                y = self.buf[self.offs[b[t]]:self.offs[b[t] + 1]].tobytes()
+                dr = oracle.nw(x, oracle.compl_reverse(y), "myers")
+                if dr <= int(dpass[L[t]]):
+                    rows.append((i, int(js[t]), dr, 1))
+        rows.sort()
+        recs = np.array(rows, dtype=RECORD) if rows else np.empty(0, dtype=RECORD)
+        tot = {"pairs": pairs, "n_records": len(rows), "fwd_survivors": 0, "rc_survivors": 0, "zone_checks": 0,
+               "word_updates": 0, "screen_ms": 0.0, "total_ms": 0.0, "steps": 1}
+        return recs, tot
+
+    def close(self):
+        self.closed = True

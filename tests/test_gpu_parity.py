@@ -26,9 +26,9 @@ def test_exact_distance_known_and_boundaries(engine):
     al = np.frombuffer(b"ACGT", dtype=np.uint8)
     reads = [b"A", b"C", b"ACGT", b"AGGT", b"ACGGT", b"AGT", b"AAAA", b"TTTT", b"KITTEN", b"SITTING", b"ACGTN", b"ACGTA"]
     for m in (31, 32, 33, 63, 64, 65, 95, 96, 97, 1023, 1024, 1025, 1500):
-        a = al[rng.integers(0, 4, m)]
-        reads += [a.tobytes(), a[1:].tobytes(), synth.mutate(rng, a % 4).astype(np.uint8).tobytes() if False else al[synth.mutate(rng, (a == ord("C")) * 1 + (a == ord("G")) * 2 + (a == ord("T")) * 3)].tobytes(),
-                  al[rng.integers(0, 4, m)].tobytes()]
+        c = rng.integers(0, 4, m).astype(np.uint8)
+        a = al[c]
+        reads += [a.tobytes(), a[1:].tobytes(), al[synth.mutate(rng, c)].tobytes(), al[rng.integers(0, 4, m)].tobytes()]
     buf, offs = synth.pack_reads(reads)
     engine.upload_reads(buf, offs)
     n = len(reads)
