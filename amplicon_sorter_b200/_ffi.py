@@ -16,7 +16,8 @@ ASB_OK, ASB_DONE = 0, 1
 class StepInfo(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("n_records", C.c_uint64), ("fwd_survivors", C.c_uint64),
                 ("rc_survivors", C.c_uint64), ("zone_checks", C.c_uint64), ("word_updates", C.c_uint64),
-                ("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("screen_ms", C.c_float), ("total_ms", C.c_float)]
+                ("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("screen_ms", C.c_float), ("total_ms", C.c_float),
+                ("launches", C.c_uint32), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -31,7 +32,7 @@ class EngineError(RuntimeError):
 _LIB = None
 
 SYMBOLS = ["asb_version", "asb_create", "asb_destroy", "asb_last_error", "asb_set_param", "asb_upload_reads",
-           "asb_batch_begin", "asb_batch_step", "asb_batch_records", "asb_distance_pairs", "asb_debug_read"]
+           "asb_batch_begin", "asb_batch_step", "asb_batch_records", "asb_distance_pairs", "asb_debug_read", "asb_batch_records_dev", "asb_int_peak"]
 
 
 def lib_path() -> str:
@@ -61,6 +62,8 @@ def load():
     L.asb_batch_step.argtypes = [vp, C.POINTER(StepInfo)]
     L.asb_batch_records.argtypes = [vp, vp]
     L.asb_distance_pairs.argtypes = [vp, u32p, u32p, u8p, C.c_uint64, C.c_int, i32p]
+    L.asb_batch_records_dev.argtypes = [vp, vp]
+    L.asb_int_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.asb_debug_read.argtypes = [vp, C.c_uint32, C.c_int, u8p, C.c_uint32]
     _LIB = L
     return L

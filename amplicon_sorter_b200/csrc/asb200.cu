@@ -314,6 +314,46 @@ __global__ void asb_encode(const uint8_t* __restrict__ ascii, const uint64_t* __
     }
 }
 
+// INT32 ALU-pipe roofline probe: 16 independent dependency chains per thread.
+// which == 0: pure LOP3 (x = (x & a) ^ b);  which == 1: the Myers mix (7 LOP3 : 1 LEA/IADD3 : 2 SHF).
+__global__ void __launch_bounds__(256) asb_int_peak_kernel(uint32_t* __restrict__ sink, int iters, int which)
+{
+    uint32_t x[16];
+    const uint32_t a = 0x9E3779B9u ^ threadIdx.x, b = 0x85EBCA6Bu + blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = a * (i + 1) + b;
+    if (which == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = (x[i] & x[(i + 5) & 15]) ^ x[(i + 11) & 15];  // one LOP3, three live inputs
+            }
+        }
+    } else {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t u = x[(i + 5) & 15], w = x[(i + 11) & 15], z = x[(i + 3) & 15];
+                uint32_t v = x[i];
+                v = (v & u) ^ w;               // LOP3
+                v = __funnelshift_l(u, v, 1);  // SHF
+                v = (v | w) & ~z;              // LOP3
+                v = v + u + w;                 // IADD3
+                v = (v ^ z) | u;               // LOP3
+                v = __funnelshift_l(w, v, 1);  // SHF
+                v = (v & z) ^ u;               // LOP3
+                v = v + (w >> 31);             // LEA.HI / IADD3
+                x[i] = (v | u) & w;            // LOP3
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc ^= x[i];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 }  // namespace asb
 
 // ================================================================================================
@@ -390,6 +430,7 @@ struct asb_ctx {
     // last step's sorted records on device
     uint64_t* rec_keys = nullptr; uint32_t* rec_vals = nullptr; uint64_t rec_n = 0;
     asb_record* h_stage = nullptr; size_t h_stage_n = 0;  // pinned staging
+    uint32_t launches = 0;  // own kernels launched since the last step began
     DevBuf<asb_record> d_rec;
 };
 
@@ -493,6 +534,7 @@ int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint3
     grid = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint64_t>(blocks, 1));
     fn<<<grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(B, mode);
     CU(cudaGetLastError());
+    ctx->launches++;
     return ASB_OK;
 }
 
@@ -682,6 +724,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     if (!ctx->in_batch) return fail(ctx, ASB_E_ARG, "asb_batch_step without asb_batch_begin");
     CU(cudaSetDevice(ctx->device));
     memset(info, 0, sizeof *info);
+    ctx->launches = 0;
     const uint32_t n = ctx->n;
     // skip rows without partners
     uint32_t r0 = ctx->next_row;
@@ -744,6 +787,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
         grid = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint64_t>(blocks, 1));
         fn<<<grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(B);
         CU(cudaGetLastError());
+        ctx->launches++;
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     rc = read_counters(ctx);
@@ -800,6 +844,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     info->n_records = nO;
     info->word_updates = ctx->h_ctr[C_WORDS] * 32ull;
     info->row_begin = r0; info->row_end = r1;
+    info->launches = ctx->launches;
     ctx->next_row = r1;
     return ASB_OK;
 }
@@ -816,6 +861,48 @@ int asb_batch_records(asb_ctx* ctx, asb_record* dst)
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(dst, ctx->d_rec.p, sizeof(asb_record) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    return ASB_OK;
+}
+
+int asb_batch_records_dev(asb_ctx* ctx, asb_record* dev_dst)
+{
+    if (!ctx) return ASB_E_ARG;
+    if (ctx->rec_n == 0) return ASB_OK;
+    if (!dev_dst) return fail(ctx, ASB_E_ARG, "null destination");
+    CU(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->rec_n;
+    asb_pack_records<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->rec_keys, ctx->rec_vals, n, dev_dst);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASB_OK;
+}
+
+int asb_int_peak(asb_ctx* ctx, int iters, double* lop3_tops, double* mix_tops)
+{
+    if (!ctx || !lop3_tops || !mix_tops || iters < 1) return fail(ctx, ASB_E_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf<uint32_t> sink;
+    struct Guard { DevBuf<uint32_t>& a; ~Guard() { a.release(); } } guard{sink};
+    const int grid = ctx->sm_count * 8, block = 256;
+    CU(sink.ensure((size_t)grid * block));
+    double out[2] = {0, 0};
+    for (int which = 0; which < 2; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+            asb_int_peak_kernel<<<grid, block, 0, ctx->stream>>>(sink.p, iters, which);
+            CU(cudaGetLastError());
+            CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+            if (rep > 0) best = std::min(best, ms);
+        }
+        // 16 chains x 8 LOP3 (which 0) or 16 chains x 9 ALU ops (which 1) per iteration per thread
+        out[which] = (double)grid * block * (double)iters * 16.0 * (which ? 9.0 : 8.0) / (best * 1e-3) / 1e12;
+    }
+    *lop3_tops = out[0];
+    *mix_tops = out[1];
     return ASB_OK;
 }
 

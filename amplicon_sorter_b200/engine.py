@@ -85,6 +85,16 @@ class Engine:
             self._check(self._lib.asb_batch_records(self._h, out.ctypes.data))
         return out
 
+    def batch_records_dev(self, dev_ptr: int):
+        """Copy the last step's records into device memory at `dev_ptr` (same GPU)."""
+        self._check(self._lib.asb_batch_records_dev(self._h, C.c_void_p(dev_ptr)))
+
+    def int_peak(self, iters: int = 2000):
+        """(pure LOP3, Myers-mix) INT32 ALU throughput of this GPU in 1e12 lane-ops/s, measured live."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self._lib.asb_int_peak(self._h, iters, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def compare_batch(self, order, hi, dpass, drev, rank=0, world=1, fetch=True):
         """All steps of one batch.  Returns (records sorted by (i_pos, j_pos), totals dict)."""
         self.batch_begin(order, hi, dpass, drev, rank, world)

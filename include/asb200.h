@@ -51,6 +51,8 @@ typedef struct {
     uint32_t row_begin, row_end; /* rows [row_begin,row_end) of the sorted batch covered */
     float screen_ms;         /* device time of the dominant kernel (asb_screen) in this step */
     float total_ms;          /* device time of the whole step */
+    uint32_t launches;       /* this library's own kernels launched by the step (cub sorts not counted) */
+    uint32_t reserved;
 } asb_step_info;
 
 /* Replaces nothing in the reference (it has no device): create/destroy an engine on `device`.
@@ -80,6 +82,13 @@ int asb_batch_begin(asb_ctx *ctx, const uint32_t *order, uint32_t n, const uint3
 int asb_batch_step(asb_ctx *ctx, asb_step_info *info);
 /* Copies the records of the last step (info.n_records of them) to host memory. */
 int asb_batch_records(asb_ctx *ctx, asb_record *dst);
+
+/* Same, into DEVICE memory on the context's device (for an NCCL gather of the per-GPU lists). */
+int asb_batch_records_dev(asb_ctx *ctx, asb_record *dev_dst);
+
+/* Measurement aid: live INT32 ALU-pipe throughput of this GPU in 1e12 lane-operations/s -- pure
+ * LOP3 and the instruction mix of the Myers word-update -- the roofline the path is bound by. */
+int asb_int_peak(asb_ctx *ctx, int iters, double *lop3_tops, double *mix_tops);
 
 /* Replaces distance(X1, X2, mode) (:224-234) on an explicit pair list of uploaded read ids:
  * out_d[p] = exact edit distance, NW (mode 0) between a[p] and b[p] (shorter one is the query);
