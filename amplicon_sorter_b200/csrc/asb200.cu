@@ -157,8 +157,10 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         return;
     }
     BandGeom g;
-    g.BL = (Dmax + 31) >> 5;
-    const int need = g.BL + ((Emax + 31) >> 5) + 1;
+    g.Dmax = Dmax;
+    g.Emax = Emax;
+    g.T0 = (31 + Emax) >> 5;  // rows <= 32 + Emax
+    const int need = ((Dmax + 31) >> 5) + ((Emax + 31) >> 5) + 1;
     g.Bw = BT > 0 ? BT : min(need, max(W, 1));
     if ((BT > 0 && need > BT && W > BT) || (BT == 0 && g.Bw > kMaxDynWords)) {
         atomicOr(&B.ctr[C_ERR], (unsigned long long)E_BAND);
@@ -174,32 +176,35 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
     }
     build_peq(peq, B, q, m, W);
 
-    int st, sc;
-    if (mode == M_SCREEN || mode == M_FWD || mode == M_ZONE || mode == M_EXACT) {
-        const uint8_t* t = (mode == M_EXACT && job.strand) ? tr : tf;
+    // One call site for both strands (keeps a single copy of the unrolled pass in the instruction cache).
+#pragma unroll 1
+    for (int phase = (mode == M_RC ? 1 : 0); phase < 2; ++phase) {
+        const uint8_t* t = (phase == 1 || (mode == M_EXACT && job.strand)) ? tr : tf;
+        int st, sc;
         band_pass<BT>(peq, B.Wpad, W, m, t, n, k, ok, g, push, st, sc, cols_acc);
-        if (mode == M_EXACT) {
-            if (job.valid) B.ex_out[job.entry] = (st == PASS_DONE) ? sc : -1;
-            return;
-        }
         const bool pass = ok && st == PASS_DONE && sc <= k;
-        if (mode == M_ZONE) {  // emit the reverse record iff d_fwd > drev-1  (iden_fwd < 0.5, AS:794)
-            warp_push(job.valid && !pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, (job.zval << 1) | 1u, &B.ctr[C_ERR]);
-            return;
-        }
-        warp_push(pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, ((uint32_t)sc << 1), &B.ctr[C_ERR]);  // AS:791-793
         const bool surv = ok && st == PASS_SURVIVOR;
-        if (mode == M_SCREEN) warp_push(surv, B.F, nullptr, &B.ctr[C_F], B.list_cap, key, 0u, &B.ctr[C_ERR]);
-        const bool need_rc = ok && !pass && !surv;  // proven d_fwd > dpass
-        if (mode == M_FWD) { warp_push(need_rc, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]); return; }
-        ok = need_rc;
-        if (__ballot_sync(0xFFFFFFFFu, ok) == 0u) return;
+        if (phase == 0) {
+            if (mode == M_EXACT) {
+                if (job.valid) B.ex_out[job.entry] = (st == PASS_DONE) ? sc : -1;
+                return;
+            }
+            if (mode == M_ZONE) {  // emit the reverse record iff d_fwd > drev-1  (iden_fwd < 0.5, AS:794)
+                warp_push(job.valid && !pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, (job.zval << 1) | 1u, &B.ctr[C_ERR]);
+                return;
+            }
+            warp_push(pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, ((uint32_t)sc << 1), &B.ctr[C_ERR]);  // AS:791-793
+            if (mode == M_SCREEN) warp_push(surv, B.F, nullptr, &B.ctr[C_F], B.list_cap, key, 0u, &B.ctr[C_ERR]);
+            const bool need_rc = ok && !pass && !surv;  // proven d_fwd > dpass
+            if (mode == M_FWD) { warp_push(need_rc, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]); return; }
+            ok = need_rc;
+            if (__ballot_sync(0xFFFFFFFFu, ok) == 0u) return;
+        } else {
+            // compl_reverse strand (AS:795): same band, k = dpass
+            warp_push(pass, B.Z, B.Zv, &B.ctr[C_Z], B.list_cap, key, (uint32_t)sc, &B.ctr[C_ERR]);
+            if (mode == M_SCREEN) warp_push(surv, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]);
+        }
     }
-    // ---- compl_reverse strand (AS:795): same band, k = dpass
-    band_pass<BT>(peq, B.Wpad, W, m, tr, n, k, ok, g, push, st, sc, cols_acc);
-    const bool rpass = ok && st == PASS_DONE && sc <= k;
-    warp_push(rpass, B.Z, B.Zv, &B.ctr[C_Z], B.list_cap, key, (uint32_t)sc, &B.ctr[C_ERR]);
-    if (mode == M_SCREEN) warp_push(ok && st == PASS_SURVIVOR, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -363,7 +368,7 @@ using namespace asb;
 
 namespace {
 
-constexpr int kClasses[] = {3, 5, 7, 9, 11, 13, 15, 17, 20, 24, 28, 32, 36, 40, 0};
+constexpr int kClasses[] = {5, 9, 13, 17, 24, 32, 40, 0};
 constexpr int kNumClasses = sizeof(kClasses) / sizeof(int);
 constexpr int kWarpsPerBlock = 8;
 
@@ -374,7 +379,7 @@ template <int... Bs> struct FnTable {
     static screen_fn screen(int idx) { static const screen_fn t[] = {asb_screen<Bs>...}; return t[idx]; }
     static lists_fn lists(int idx) { static const lists_fn t[] = {asb_lists<Bs>...}; return t[idx]; }
 };
-using Fns = FnTable<3, 5, 7, 9, 11, 13, 15, 17, 20, 24, 28, 32, 36, 40, 0>;
+using Fns = FnTable<5, 9, 13, 17, 24, 32, 40, 0>;
 
 int class_for(int need)
 {

@@ -23,9 +23,11 @@ constexpr int kMaxDynWords = 512;  // BT == 0: window words kept in local memory
 enum PassStatus : int { PASS_DEAD = 0, PASS_DONE = 1, PASS_SURVIVOR = 2 };
 
 struct BandGeom {
-    int BL;     // words kept above the word that holds row c (Ukkonen "D" side)
-    int Bw;     // window words actually iterated (== BT when BT > 0)
+    int Dmax;   // max over lanes of (n-m)+e : band reaches rows >= c - Dmax
+    int Emax;   // max over lanes of e       : band reaches rows <= c + Emax
+    int Bw;     // window words available (== BT when BT > 0)
     int ncols;  // warp-uniform number of columns to run (multiple of 32)
+    int T0;     // last word the first 32 columns can touch
 };
 
 // One Myers word-update.  hin arrives as the top bits of the previous word's Ph/Mh (php/mhp) so
@@ -48,106 +50,186 @@ struct BandGeom {
         (MHP) = mh_;                                          \
     }
 
+// Granularity of the straight-line variants: active lengths are rounded up to BT - j*step.
+__host__ __device__ constexpr int len_step(int BT) { return BT <= 9 ? 1 : (BT <= 17 ? 2 : 4); }
+
+// 32 columns over the first LEN words of the window, straight-line (no per-word control flow).
+template <int LEN, int NB>
+__device__ __forceinline__ void cols32_fast(uint32_t (&Pv)[NB], uint32_t (&Mv)[NB], const uint32_t* __restrict__ peqb,
+                                            const int Wpad, const uint32_t* __restrict__ tgt32, uint32_t& nxt, int& S)
+{
+    // two columns per iteration: the union of all LEN variants must stay inside the instruction
+    // cache (a 4-column unroll of 9 variants thrashed it: ncu stall_no_instruction = 15 per issue)
+    uint32_t cw = 0;
+#pragma unroll 1
+    for (int q = 0; q < 16; ++q) {
+        if ((q & 1) == 0) { cw = nxt; nxt = __ldg(tgt32 + (q >> 1) + 1); }
+        else cw >>= 16;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const uint32_t sym = (cw >> (8 * s)) & 0xFFu;
+            const uint32_t* __restrict__ row = peqb + sym * Wpad;
+            uint32_t php = 0x80000000u, mhp = 0u, hmb = 0u;  // hin = +1 above the first active word
+#pragma unroll
+            for (int t = 0; t < LEN; ++t) ASB_WORD_UPDATE(row[t], Pv[t], Mv[t], php, mhp, hmb)
+            S += (int)(php >> 31) - (int)(mhp >> 31);
+        }
+    }
+}
+
+template <int BT, int LEN, int NB>
+__device__ __forceinline__ void cols32_dispatch(const int len, uint32_t (&Pv)[NB], uint32_t (&Mv)[NB],
+                                                const uint32_t* __restrict__ peqb, const int Wpad,
+                                                const uint32_t* __restrict__ tgt32, uint32_t& nxt, int& S)
+{
+    constexpr int STEP = len_step(BT);
+    if constexpr (LEN - STEP >= 1) {
+        if (len <= LEN - STEP) { cols32_dispatch<BT, LEN - STEP, NB>(len, Pv, Mv, peqb, Wpad, tgt32, nxt, S); return; }
+    }
+    cols32_fast<LEN, NB>(Pv, Mv, peqb, Wpad, tgt32, nxt, S);
+}
+
 // Runs one banded pass for the 32 lanes of a warp (must be called by all 32 lanes).
-//   peq    : shared memory, row `sym` at peq + sym*Wpad, W real words then zero padding
+//   peq    : shared memory, row `sym` at peq + sym*Wpad, W real words then >= BT zero words
 //   m, W   : query length and ceil(m/32) (warp-uniform), m >= 1
 //   tgt    : this lane's target symbol codes (16-byte aligned, padded with the zero-row symbol)
 //   n, k   : this lane's target length (n >= m) and threshold; on = lane participates
 //   g      : warp-uniform band geometry (every participating lane's band fits in it)
-//   push_thresh / allow_stop : screening -- stop at a 32-column boundary once at most push_thresh
-//            lanes are undecided (they are reported as PASS_SURVIVOR)
+//   push_thresh : screening -- stop at a 32-column boundary once at most push_thresh lanes are
+//            undecided (they are reported as PASS_SURVIVOR)
 // Returns status (per lane) and, for PASS_DONE, the score D'[m][n].
-// work accumulates columns x window words executed per lane (warp-uniform) for the work counters.
+// work accumulates columns x active words executed per lane (warp-uniform) for the work counters.
+//
+// Active range.  The registers Pv[0..len) / Mv[0..len) hold the words base .. base+len-1; nothing
+// else is computed.  For a cell let LB(r, c) = D'[r][c] + |r - r*(c)|, r*(c) = m - (n - c): no path
+// through a cell with LB > k ends with cost <= k.  D' is non-decreasing along diagonals and
+// |r - r*| is constant along them, so LB is non-decreasing along diagonals; the cells of word t in
+// columns (c, c+32] lie on diagonals that cross column c inside words t-1 and t.  Hence, with
+// "alive" = the word may hold a cell with LB <= k for some undecided lane (word-level test:
+// min D' >= (A + B - 32)/2 for boundary scores A, B), the next 32 columns need exactly the words
+// [first alive, last alive + 1], intersected with Ukkonen's band for those columns.  Words dropped
+// at the top never come back; a word (re-)entering at the bottom starts from Pv = all-ones (vertical
+// +1 edges below the word above): an upper bound that is exact wherever a cost <= k path can run.
 template <int BT>
 __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, const int Wpad, const int W, const int m,
-                                          const uint8_t* __restrict__ tgt, const int n, const int k, const bool on,
-                                          const BandGeom g, const int push_thresh, int& status, int& score,
-                                          unsigned long long& work)
+                                       const uint8_t* __restrict__ tgt, const int n, const int k, const bool on,
+                                       const BandGeom g, const int push_thresh, int& status, int& score,
+                                       unsigned long long& work)
 {
     constexpr int NB = BT > 0 ? BT : kMaxDynWords;
-    const int Bw = BT > 0 ? BT : g.Bw;
+    constexpr int STEP = len_step(BT);
+    const int Bmax = BT > 0 ? BT : g.Bw;
     uint32_t Pv[NB], Mv[NB];
+    const int wm = (m - 1) >> 5;  // word holding row m
+    int base = 0;                 // absolute index of word Pv[0]
+    int len = min(min(Bmax, g.T0 + 1), wm + 1);
+    if (BT > 0) len = min(BT, BT - ((BT - len) / STEP) * STEP);
 #pragma unroll
-    for (int t = 0; t < Bw; ++t) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; }
-
-    const int maxbase = W > Bw ? W - Bw : 0;
-    int base = 0;
-    int S = 32 * Bw;  // D'[32*(base+Bw)][c]: score on the window's bottom boundary
+    for (int t = 0; t < Bmax; ++t) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; }
+    int S = 32 * len;  // D'[32*(base+len)][c]: score on the active range's bottom boundary
     bool alive = on;
     status = PASS_DEAD;
     score = 0;
-    const int wm = (m - 1) >> 5;                                        // word holding row m
     const uint32_t himask = ~(((m - 1) & 31) == 31 ? 0xFFFFFFFFu : ((2u << ((m - 1) & 31)) - 1u));  // rows below m in that word
     const uint32_t* tgt32 = reinterpret_cast<const uint32_t*>(tgt);
     const int nblocks = g.ncols >> 5;
     uint32_t nxt = __ldg(tgt32);
     int c = 0;
     for (int cb = 0; cb < nblocks; ++cb) {
-        // ---- slide the window one word down when the band has moved on
-        int nb = cb - g.BL;
-        nb = nb < 0 ? 0 : (nb > maxbase ? maxbase : nb);
-        if (nb != base) {
+        const uint32_t* __restrict__ peqb = peq + base;
+        // does any undecided lane reach its last column inside this block?
+        const bool fin = __any_sync(0xFFFFFFFFu, alive && n <= c + 32);
+        if (BT > 0 && !fin) {
+            cols32_dispatch<BT, (BT > 0 ? BT : 1), NB>(len, Pv, Mv, peqb, Wpad, tgt32 + cb * 8, nxt, S);
+            c += 32;
+        } else {
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t cw = nxt;
+                nxt = __ldg(tgt32 + cb * 8 + q + 1);
 #pragma unroll
-            for (int t = 0; t + 1 < Bw; ++t) { Pv[t] = Pv[t + 1]; Mv[t] = Mv[t + 1]; }
-            Pv[Bw - 1] = 0xFFFFFFFFu;
-            Mv[Bw - 1] = 0u;
-            S += 32;
-            base = nb;
-        }
-        // ---- 32 columns
-        for (int q = 0; q < 8; ++q) {
-            const uint32_t cw = nxt;
-            nxt = __ldg(tgt32 + cb * 8 + q + 1);
+                for (int s = 0; s < 4; ++s) {
+                    const uint32_t sym = (cw >> (8 * s)) & 0xFFu;
+                    const uint32_t* __restrict__ row = peqb + sym * Wpad;
+                    uint32_t php = 0x80000000u, mhp = 0u, hmb = 0u;
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const uint32_t sym = (cw >> (8 * s)) & 0xFFu;
-                const uint32_t* __restrict__ row = peq + sym * Wpad + base;
-                uint32_t php = 0x80000000u, mhp = 0u, hmb = 0u;  // hin = +1 above the window
-#pragma unroll
-                for (int t = 0; t < Bw; ++t) ASB_WORD_UPDATE(row[t], Pv[t], Mv[t], php, mhp, hmb)
-                S += (int)(php >> 31) - (int)(mhp >> 31);
-                ++c;
-                if (c == n && alive) {
-                    // D'[m][n] = S - (vertical deltas between row m and the window bottom)
-                    int sc = S;
-                    const int tm = wm - base;
-#pragma unroll
-                    for (int t = 0; t < Bw; ++t) {
-                        if (t > tm) sc -= __popc(Pv[t]) - __popc(Mv[t]);
-                        else if (t == tm) sc -= __popc(Pv[t] & himask) - __popc(Mv[t] & himask);
+                    for (int t = 0; t < Bmax; ++t) {
+                        if (t < len) ASB_WORD_UPDATE(row[t], Pv[t], Mv[t], php, mhp, hmb)
                     }
-                    score = sc;
-                    status = PASS_DONE;
-                    alive = false;
+                    S += (int)(php >> 31) - (int)(mhp >> 31);
+                    ++c;
+                    if (c == n && alive) {
+                        // D'[m][n] = S - (vertical deltas between row m and the active bottom)
+                        int sc = S;
+                        const int tm = wm - base;
+#pragma unroll
+                        for (int t = 0; t < Bmax; ++t) {
+                            if (t > tm && t < len) sc -= __popc(Pv[t]) - __popc(Mv[t]);
+                            else if (t == tm) sc -= __popc(Pv[t] & himask) - __popc(Mv[t] & himask);
+                        }
+                        if (tm >= 0 && tm < len) { score = sc; status = PASS_DONE; }  // else (m, n) is provably > k
+                        alive = false;
+                    }
                 }
             }
         }
-        work += 32ull * (unsigned)Bw;
-        // ---- can any path through this column still finish with cost <= k ?
-        // For word t (rows lo..lo+31, boundary scores A above and Bv below):
-        //   min D' >= (A + Bv - 32)/2, and reaching (m, n) from row r costs >= |r - r*|,
-        //   r* = m - (n - c) being the row of the goal diagonal in this column.
+        work += 32ull * (unsigned)len;
+        // ---- which words can still carry a path of cost <= k ?
+        int fa = 0x7FFFFFFF, la = -1;
         if (alive) {
             const int rstar = m - (n - c);
             int bsb = S;
-            bool any = false;
 #pragma unroll
-            for (int t = Bw - 1; t >= 0; --t) {
-                const int bst = bsb - __popc(Pv[t]) + __popc(Mv[t]);
-                const int lo = 32 * (base + t) + 1, hi = lo + 31;
-                int gd = lo - rstar;
-                const int gd2 = rstar - hi;
-                gd = gd > gd2 ? gd : gd2;
-                gd = gd > 0 ? gd : 0;
-                const int lb = ((bst + bsb - 32 + 1) >> 1) + gd;
-                any = any || (lb <= k);
-                bsb = bst;
+            for (int t = Bmax - 1; t >= 0; --t) {
+                if (t < len) {
+                    const int bst = bsb - __popc(Pv[t]) + __popc(Mv[t]);
+                    const int lo = 32 * (base + t) + 1, hi = lo + 31;
+                    int gd = lo - rstar;
+                    const int gd2 = rstar - hi;
+                    gd = gd > gd2 ? gd : gd2;
+                    gd = gd > 0 ? gd : 0;
+                    const int lb = ((bst + bsb - 32 + 1) >> 1) + gd;
+                    if (lb <= k) { fa = t; la = la < 0 ? t : la; }
+                    bsb = bst;
+                }
             }
-            alive = any;
+            alive = la >= 0;
         }
         const unsigned am = __ballot_sync(0xFFFFFFFFu, alive);
         if (am == 0u) break;
         if (__popc(am) <= push_thresh) break;
+        // ---- active range of the next block (absolute word indices), clipped to Ukkonen's band
+        int ntop = base + __reduce_min_sync(0xFFFFFFFFu, fa);
+        int nbot = base + __reduce_max_sync(0xFFFFFFFFu, la) + 1;
+        // rows needed by columns c+1 .. c+32: [c+1-Dmax, c+32+Emax]
+        const int gtop = (c - g.Dmax) > 0 ? (c - g.Dmax) >> 5 : 0;
+        const int gbot = min(wm, (c + 31 + g.Emax) >> 5);
+        ntop = max(ntop, gtop);
+        nbot = min(nbot, gbot);
+        // row 0 (D[0][c] = c) is a boundary, not a word: diagonals leaving it inside the next block enter
+        // word 0, and its cells can be live up to column Dmax -- keep word 0 until then
+        if (c < g.Dmax + 1) ntop = 0;
+        if (nbot < ntop) break;  // nothing live inside the band: every undecided lane is > k
+        int nlen = nbot - ntop + 1;
+        if (BT > 0) nlen = min(BT, BT - ((BT - nlen) / STEP) * STEP);  // round up to a compiled variant
+        nlen = min(nlen, Bmax);
+        // drop dead words at the top: shift the registers
+        for (int d = ntop - base; d > 0; --d) {
+#pragma unroll
+            for (int t = 0; t + 1 < Bmax; ++t) { Pv[t] = Pv[t + 1]; Mv[t] = Mv[t + 1]; }
+            --len;
+        }
+        base = ntop;
+        // shrink the bottom: S moves up to the new bottom boundary
+#pragma unroll
+        for (int t = Bmax - 1; t >= 0; --t) {
+            if (t >= nlen && t < len) S -= __popc(Pv[t]) - __popc(Mv[t]);
+        }
+        // grow the bottom: words entering start from vertical +1 edges
+#pragma unroll
+        for (int t = 0; t < Bmax; ++t) {
+            if (t >= len && t < nlen) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; S += 32; }
+        }
+        len = nlen;
     }
     if (alive) status = PASS_SURVIVOR;
 }
