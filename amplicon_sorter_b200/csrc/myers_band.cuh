@@ -33,6 +33,10 @@ struct BandGeom {
 // One Myers word-update.  hin arrives as the top bits of the previous word's Ph/Mh (php/mhp) so
 // the horizontal +-1 is injected by the funnel shift itself; a negative hin is also the carry-in
 // of the addition:  (((Eq|h)&Pv)+Pv)^Pv | (Eq|h)  ==  ((Eq&Pv)+Pv+h)^Pv | Eq   for h in {0,1}.
+#ifndef ASB_FMA_OFFLOAD
+#define ASB_FMA_OFFLOAD 0  // measured on B200: IMAD.HI.U32 is too slow, 247 vs 254 M pairs/s -- kept for the record
+#endif
+#if ASB_FMA_OFFLOAD == 0
 #define ASB_WORD_UPDATE(EQ, PV, MV, PHP, MHP, HMB)            \
     {                                                         \
         const uint32_t eq_ = (EQ);                            \
@@ -49,6 +53,34 @@ struct BandGeom {
         (PHP) = ph_;                                          \
         (MHP) = mh_;                                          \
     }
+#else
+// The INT32 ALU pipe (LOP3/SHF/IADD3/LEA) is the roofline; the FMA pipe idles.  Shifts and carries
+// are therefore written as integer multiply-adds, which ptxas keeps on the FMA pipe:
+//   x >> 31        ->  mul.hi.u32 x, 2        (IMAD.HI.U32)
+//   (x << 1) | bit ->  mad.lo.u32 x, 2, bit   (IMAD)
+//   a + b          ->  mad.lo.u32 a, 1, b     (IMAD.IADD)
+// leaving 7 LOP3 per word-update on the ALU pipe.  PHP/MHP carry the BITS (0/1) here, not the words.
+__device__ __forceinline__ uint32_t asb_topbit(uint32_t x) { uint32_t r; asm("mul.hi.u32 %0, %1, 2;" : "=r"(r) : "r"(x)); return r; }
+__device__ __forceinline__ uint32_t asb_shl1_or(uint32_t x, uint32_t bit) { uint32_t r; asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(r) : "r"(x), "r"(bit)); return r; }
+__device__ __forceinline__ uint32_t asb_add(uint32_t a, uint32_t b) { uint32_t r; asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+#define ASB_WORD_UPDATE(EQ, PV, MV, PHP, MHP, HMB)                     \
+    {                                                                  \
+        const uint32_t eq_ = (EQ);                                     \
+        const uint32_t xv_ = eq_ | (MV);                               \
+        const uint32_t hpb_ = asb_topbit(PHP);                         \
+        const uint32_t hmb_ = asb_topbit(MHP);                         \
+        const uint32_t s_ = asb_add(asb_add(eq_ & (PV), (PV)), hmb_);  \
+        const uint32_t xh_ = (s_ ^ (PV)) | eq_;                        \
+        const uint32_t ph_ = (MV) | ~(xh_ | (PV));                     \
+        const uint32_t mh_ = (PV) & xh_;                               \
+        const uint32_t ph2_ = asb_shl1_or(ph_, hpb_);                  \
+        const uint32_t mh2_ = asb_shl1_or(mh_, hmb_);                  \
+        (PV) = mh2_ | ~(xv_ | ph2_);                                   \
+        (MV) = ph2_ & xv_;                                             \
+        (PHP) = ph_;                                                   \
+        (MHP) = mh_;                                                   \
+    }
+#endif
 
 // Granularity of the straight-line variants: active lengths are rounded up to BT - j*step.
 __host__ __device__ constexpr int len_step(int BT) { return BT <= 9 ? 1 : (BT <= 17 ? 2 : 4); }
@@ -56,7 +88,7 @@ __host__ __device__ constexpr int len_step(int BT) { return BT <= 9 ? 1 : (BT <=
 // 32 columns over the first LEN words of the window, straight-line (no per-word control flow).
 template <int LEN, int NB>
 __device__ __forceinline__ void cols32_fast(uint32_t (&Pv)[NB], uint32_t (&Mv)[NB], const uint32_t* __restrict__ peqb,
-                                            const int Wpad, const uint32_t* __restrict__ tgt32, uint32_t& nxt, int& S)
+                                            const int Wpad, const uint32_t* __restrict__ tgt32, uint32_t& nxt)
 {
     // two columns per iteration: the union of all LEN variants must stay inside the instruction
     // cache (a 4-column unroll of 9 variants thrashed it: ncu stall_no_instruction = 15 per issue)
@@ -67,12 +99,11 @@ __device__ __forceinline__ void cols32_fast(uint32_t (&Pv)[NB], uint32_t (&Mv)[N
         else cw >>= 16;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
-            const uint32_t sym = (cw >> (8 * s)) & 0xFFu;
+            const uint32_t sym = __byte_perm(cw, 0u, 0x4440u + s);
             const uint32_t* __restrict__ row = peqb + sym * Wpad;
             uint32_t php = 0x80000000u, mhp = 0u, hmb = 0u;  // hin = +1 above the first active word
 #pragma unroll
             for (int t = 0; t < LEN; ++t) ASB_WORD_UPDATE(row[t], Pv[t], Mv[t], php, mhp, hmb)
-            S += (int)(php >> 31) - (int)(mhp >> 31);
         }
     }
 }
@@ -80,13 +111,13 @@ __device__ __forceinline__ void cols32_fast(uint32_t (&Pv)[NB], uint32_t (&Mv)[N
 template <int BT, int LEN, int NB>
 __device__ __forceinline__ void cols32_dispatch(const int len, uint32_t (&Pv)[NB], uint32_t (&Mv)[NB],
                                                 const uint32_t* __restrict__ peqb, const int Wpad,
-                                                const uint32_t* __restrict__ tgt32, uint32_t& nxt, int& S)
+                                                const uint32_t* __restrict__ tgt32, uint32_t& nxt)
 {
     constexpr int STEP = len_step(BT);
     if constexpr (LEN - STEP >= 1) {
-        if (len <= LEN - STEP) { cols32_dispatch<BT, LEN - STEP, NB>(len, Pv, Mv, peqb, Wpad, tgt32, nxt, S); return; }
+        if (len <= LEN - STEP) { cols32_dispatch<BT, LEN - STEP, NB>(len, Pv, Mv, peqb, Wpad, tgt32, nxt); return; }
     }
-    cols32_fast<LEN, NB>(Pv, Mv, peqb, Wpad, tgt32, nxt, S);
+    cols32_fast<LEN, NB>(Pv, Mv, peqb, Wpad, tgt32, nxt);
 }
 
 // Runs one banded pass for the 32 lanes of a warp (must be called by all 32 lanes).
@@ -126,11 +157,14 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
     if (BT > 0) len = min(BT, BT - ((BT - len) / STEP) * STEP);
 #pragma unroll
     for (int t = 0; t < Bmax; ++t) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; }
-    int S = 32 * len;  // D'[32*(base+len)][c]: score on the active range's bottom boundary
+    // Score bookkeeping: the boundary above word Pv[0] (row 32*base: row 0, or a dropped word's last
+    // row that is only reachable horizontally) grows by exactly +1 per column, so D'[32*base][c] =
+    // topoff + c and every other score is a popcount sum below it -- nothing to track per column.
+    int topoff = 0;
     bool alive = on;
     status = PASS_DEAD;
     score = 0;
-    const uint32_t himask = ~(((m - 1) & 31) == 31 ? 0xFFFFFFFFu : ((2u << ((m - 1) & 31)) - 1u));  // rows below m in that word
+    const uint32_t lomask = ((m - 1) & 31) == 31 ? 0xFFFFFFFFu : ((2u << ((m - 1) & 31)) - 1u);  // rows <= m in that word
     const uint32_t* tgt32 = reinterpret_cast<const uint32_t*>(tgt);
     const int nblocks = g.ncols >> 5;
     uint32_t nxt = __ldg(tgt32);
@@ -140,7 +174,7 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
         // does any undecided lane reach its last column inside this block?
         const bool fin = __any_sync(0xFFFFFFFFu, alive && n <= c + 32);
         if (BT > 0 && !fin) {
-            cols32_dispatch<BT, (BT > 0 ? BT : 1), NB>(len, Pv, Mv, peqb, Wpad, tgt32 + cb * 8, nxt, S);
+            cols32_dispatch<BT, (BT > 0 ? BT : 1), NB>(len, Pv, Mv, peqb, Wpad, tgt32 + cb * 8, nxt);
             c += 32;
         } else {
             for (int q = 0; q < 8; ++q) {
@@ -155,16 +189,15 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
                     for (int t = 0; t < Bmax; ++t) {
                         if (t < len) ASB_WORD_UPDATE(row[t], Pv[t], Mv[t], php, mhp, hmb)
                     }
-                    S += (int)(php >> 31) - (int)(mhp >> 31);
                     ++c;
                     if (c == n && alive) {
-                        // D'[m][n] = S - (vertical deltas between row m and the active bottom)
-                        int sc = S;
+                        // D'[m][n] = D'[32*base][n] + (vertical deltas down to row m)
+                        int sc = topoff + c;
                         const int tm = wm - base;
 #pragma unroll
                         for (int t = 0; t < Bmax; ++t) {
-                            if (t > tm && t < len) sc -= __popc(Pv[t]) - __popc(Mv[t]);
-                            else if (t == tm) sc -= __popc(Pv[t] & himask) - __popc(Mv[t] & himask);
+                            if (t < tm) sc += __popc(Pv[t]) - __popc(Mv[t]);
+                            else if (t == tm) sc += __popc(Pv[t] & lomask) - __popc(Mv[t] & lomask);
                         }
                         if (tm >= 0 && tm < len) { score = sc; status = PASS_DONE; }  // else (m, n) is provably > k
                         alive = false;
@@ -177,19 +210,19 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
         int fa = 0x7FFFFFFF, la = -1;
         if (alive) {
             const int rstar = m - (n - c);
-            int bsb = S;
+            int bst = topoff + c;  // score on the boundary above word t
 #pragma unroll
-            for (int t = Bmax - 1; t >= 0; --t) {
+            for (int t = 0; t < Bmax; ++t) {
                 if (t < len) {
-                    const int bst = bsb - __popc(Pv[t]) + __popc(Mv[t]);
+                    const int bsb = bst + __popc(Pv[t]) - __popc(Mv[t]);
                     const int lo = 32 * (base + t) + 1, hi = lo + 31;
                     int gd = lo - rstar;
                     const int gd2 = rstar - hi;
                     gd = gd > gd2 ? gd : gd2;
                     gd = gd > 0 ? gd : 0;
                     const int lb = ((bst + bsb - 32 + 1) >> 1) + gd;
-                    if (lb <= k) { fa = t; la = la < 0 ? t : la; }
-                    bsb = bst;
+                    if (lb <= k) { la = t; fa = fa > t ? t : fa; }
+                    bst = bsb;
                 }
             }
             alive = la >= 0;
@@ -212,22 +245,19 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
         int nlen = nbot - ntop + 1;
         if (BT > 0) nlen = min(BT, BT - ((BT - nlen) / STEP) * STEP);  // round up to a compiled variant
         nlen = min(nlen, Bmax);
-        // drop dead words at the top: shift the registers
+        // drop dead words at the top: the boundary moves down by their vertical deltas, registers shift
         for (int d = ntop - base; d > 0; --d) {
+            topoff += __popc(Pv[0]) - __popc(Mv[0]);
 #pragma unroll
             for (int t = 0; t + 1 < Bmax; ++t) { Pv[t] = Pv[t + 1]; Mv[t] = Mv[t + 1]; }
             --len;
         }
+        if (len < 0) { topoff += 32 * (-len); len = 0; }  // whole range replaced: boundary rows are +1 apart
         base = ntop;
-        // shrink the bottom: S moves up to the new bottom boundary
-#pragma unroll
-        for (int t = Bmax - 1; t >= 0; --t) {
-            if (t >= nlen && t < len) S -= __popc(Pv[t]) - __popc(Mv[t]);
-        }
-        // grow the bottom: words entering start from vertical +1 edges
+        // grow the bottom: words entering start from vertical +1 edges (shrinking needs no bookkeeping)
 #pragma unroll
         for (int t = 0; t < Bmax; ++t) {
-            if (t >= len && t < nlen) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; S += 32; }
+            if (t >= len && t < nlen) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; }
         }
         len = nlen;
     }
