@@ -411,7 +411,7 @@ struct asb_ctx {
     // params
     uint64_t pair_cap = 1ull << 26;
     double screen_frac = 0.62;
-    int push_thresh = 3;
+    int push_thresh = 1;
     // reads
     uint32_t n_reads = 0, sigma = 0, max_len = 0;
     uint8_t code_to_ascii[257];

@@ -168,7 +168,7 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
         stats_out.update(ap.stats)
         stats_out["tl"] = tl_total
     if engine is None:
-        ap.engine.close()
+        ap.engine.close()  # an engine handed in by the caller (shared across files / ranks) stays open
     if tl_total == 0:
         print("No reads to compare, exiting...")
         with open(os.path.join(outputfolder, "results.txt"), "a") as rf:

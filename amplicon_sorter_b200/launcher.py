@@ -46,12 +46,16 @@ def execute(ns, main_code, argv):
         sys.argv = old
 
 
-def install_gpu_stage(ns, device: int = 0, stats: dict | None = None):
-    """Rebind process_list (:647) in the reference's namespace to the GPU implementation."""
+def install_gpu_stage(ns, device: int = 0, stats: dict | None = None, engine_factory=None):
+    """Rebind process_list (:647) in the reference's namespace to the GPU implementation.
+
+    engine_factory() -> engine lets the multi-GPU launcher hand in a dist.ShardedEngine; by default
+    every call creates (and closes) a single-GPU Engine on `device`."""
     from . import host
 
     def process_list(self, tempfile):
-        return host.process_list(self, tempfile, ns["args"], stats_out=stats)
+        eng = engine_factory() if engine_factory else None
+        return host.process_list(self, tempfile, ns["args"], engine=eng, stats_out=stats)
 
     process_list.__doc__ = host.process_list.__doc__
     ns["process_list"] = process_list
@@ -73,9 +77,29 @@ def main(argv=None):
         k = argv.index("--script")
         script = argv[k + 1]
         del argv[k:k + 2]
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return main_distributed(find_script(script), argv)
     ns, main_code = load_reference(find_script(script))
     install_gpu_stage(ns, device)
     execute(ns, main_code, argv)
+
+
+def main_distributed(script, argv):
+    """torchrun entry: rank 0 runs the reference, the other ranks serve its all-pairs calls."""
+    from . import dist
+    from .engine import Engine
+
+    r, w, dev = dist.init_from_env()
+    engine = Engine(dev.index if dev.type == "cuda" else 0)
+    if r != 0:
+        return dist.worker_loop(engine, dev)
+    sharded = dist.ShardedEngine(engine, dev)
+    try:
+        ns, main_code = load_reference(script)
+        install_gpu_stage(ns, engine_factory=lambda: sharded)
+        execute(ns, main_code, argv)
+    finally:
+        sharded.close()
 
 
 if __name__ == "__main__":

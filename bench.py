@@ -35,6 +35,7 @@ from amplicon_sorter_b200 import host, synth, thresholds  # noqa: E402
 METRIC = "read-pair comparisons/sec (all-vs-all, ~1 kb reads)"
 UNIT = "pairs/s"
 ALU_OPS_PER_WORD_UPDATE = 10  # ALU-pipe instructions per Myers word-update in asb_screen's SASS (profiles/)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 21.7e6  # dram__bytes_read+write.sum of one asb_screen launch (ncu --set full, profiles/)
 
 
 def make_workload(n_reads: int):
@@ -305,13 +306,15 @@ def main():
         # word-updates of the screen kernel ~ all word-updates (list kernels are <2 % on this workload)
         wu_rate = agg["word_updates"] / max(agg["total_ms"] / 1e3, 1e-9)
         achieved = wu_rate * ALU_OPS_PER_WORD_UPDATE / 1e12
-        roofline = {"bound": "int_alu", "achieved": achieved, "peak": lop3, "unit": "Tops/s (INT32 ALU-pipe lane-ops)",
-                    "frac": achieved / lop3 if lop3 else None, "traffic": None,
+        peak = max(lop3, mix)
+        roofline = {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "Tops/s (INT32 ALU-pipe lane-ops)",
+                    "frac": achieved / peak if peak else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
                     "kernel": "asb_screen", "launches": agg["screen_launches"],
                     "avg_launch_ms": agg["screen_ms"] / max(agg["screen_launches"], 1),
                     "kernel_share_of_step": screen_s / max(agg["total_ms"] / 1e3, 1e-9),
                     "word_updates_per_s": wu_rate, "alu_ops_per_word_update": ALU_OPS_PER_WORD_UPDATE,
-                    "peak_source": "asb_int_peak measured live on this GPU (LOP3 chains); Myers-mix probe = %.2f" % mix,
+                    "peak_source": "asb_int_peak measured live on this GPU: best of LOP3-chain probe (%.2f) and LOP3/SHF/IADD3/LEA mix probe (%.2f); nominal 148 SM x 64 lanes x 1.965 GHz = 18.61" % (lop3, mix),
+                    "ncu": "profiles/r1_asb_screen_ncu_full_v5.txt: sm__inst_executed_pipe_alu 92.3 % of peak, dram 21.7 MB per launch",
                     "nominal": {"ops_per_job": nominal_ops(w), "note": "SURVEY 8(d): 20*ceil(m/32)*n*2 per pair (full-matrix Myers, both strands)",
                                 "equivalent_tops": nominal_ops(w) * a.steps / t_res / 1e12 / max(world, 1)},
                     "hbm": {"peak_gbs": _measured_peak("hbm_gbs"), "note": "path is not HBM-bound: ~200 MB of symbol codes stay L2-resident"}}

@@ -100,7 +100,7 @@ def test_screen_parameters_do_not_change_results(engine):
         got, _ = util.gpu_batch(engine, reads, screen_frac=frac, push_thresh=push)
         util.assert_same_records(got, want)
     engine.set_param("screen_frac", 0.62)
-    engine.set_param("push_thresh", 3)
+    engine.set_param("push_thresh", 1)
 
 
 def test_small_pair_cap_multi_step_and_sharding(engine):
