@@ -869,6 +869,37 @@ int asb_batch_records(asb_ctx* ctx, asb_record* dst)
     return ASB_OK;
 }
 
+// Host-side text assembly of the tempfile lines (amplicon_sorter.py:792-798).  The iden STRINGS come from
+// the caller (Python's own str(round(1 - d/L, 3))): entry lbase[L] + d of the string table.
+int64_t asb_format_records(const asb_record* recs, uint64_t n, const uint32_t* idx_sorted, const uint32_t* len_sorted,
+                           const uint64_t* lbase, uint32_t lbase_len, const uint32_t* soff, uint64_t n_strings,
+                           const char* sbuf, char* out, uint64_t cap)
+{
+    if ((n && (!recs || !idx_sorted || !len_sorted || !lbase || !soff || !sbuf)) || !out) return -1;
+    uint64_t k = 0;
+    auto put_u32 = [&](uint32_t v) {
+        char tmp[10];
+        int len = 0;
+        do { tmp[len++] = (char)('0' + v % 10); v /= 10; } while (v);
+        while (len) out[k++] = tmp[--len];
+    };
+    for (uint64_t r = 0; r < n; ++r) {
+        const asb_record& x = recs[r];
+        const uint32_t L = len_sorted[x.j_pos];
+        if (L >= lbase_len || lbase[L] == ~0ull) return -2;
+        const uint64_t e = lbase[L] + x.d;
+        if (e >= n_strings) return -2;
+        const uint32_t s0 = soff[e], s1 = soff[e + 1];
+        if (k + 32 + (s1 - s0) > cap) return -3;
+        put_u32(idx_sorted[x.i_pos]); out[k++] = ':';
+        put_u32(idx_sorted[x.j_pos]); out[k++] = ':';
+        memcpy(out + k, sbuf + s0, s1 - s0); k += s1 - s0;
+        if (x.reverse) { memcpy(out + k, ":reverse", 8); k += 8; }
+        out[k++] = '\n';
+    }
+    return (int64_t)k;
+}
+
 int asb_batch_records_dev(asb_ctx* ctx, asb_record* dev_dst)
 {
     if (!ctx) return ASB_E_ARG;

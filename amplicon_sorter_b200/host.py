@@ -36,30 +36,54 @@ def batch_geometry(lengths_sorted: np.ndarray):
     return hi.astype(np.uint32)
 
 
-def _iden_strings(lens_long: np.ndarray, d: np.ndarray):
-    """str(round(1 - d/L, 3)) per record, computed with Python's own float/round/str on the unique
-    (L, d) combinations only."""
-    key = lens_long.astype(np.uint64) << np.uint64(32) | d.astype(np.uint64)
-    uniq, inv = np.unique(key, return_inverse=True)
-    table = np.empty(uniq.shape[0], dtype=object)
-    for t, k in enumerate(uniq.tolist()):
-        L, dd = k >> 32, k & 0xFFFFFFFF
-        table[t] = str(round(1 - dd / L, 3))
-    return table[inv]
+def _iden_table(lens_sorted: np.ndarray, records: np.ndarray, dcap: np.ndarray | None = None):
+    """String table of str(round(1 - d/L, 3)) -- Python's own float/round/str, evaluated once per
+    (L, d) that can occur: every longer-read length L present in the records, d = 0 .. max d seen for it."""
+    L = lens_sorted[records["j_pos"]].astype(np.int64)
+    d = records["d"].astype(np.int64)
+    lmax = int(L.max())
+    if dcap is not None and dcap.shape[0] > lmax:
+        # emitted distances never exceed the pass cut-off of their length: no scan of d needed
+        present = np.bincount(L, minlength=lmax + 1) > 0
+        dmax = np.where(present, dcap[: lmax + 1].astype(np.int64), -1)
+    else:
+        dmax = np.zeros(lmax + 1, dtype=np.int64) - 1
+        np.maximum.at(dmax, L, d)
+    lbase = np.full(lmax + 1, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    strs, soff, n = [], [0], 0
+    for length in np.nonzero(dmax >= 0)[0].tolist():
+        lbase[length] = n
+        for dd in range(int(dmax[length]) + 1):
+            t = str(round(1 - dd / length, 3))
+            strs.append(t)
+            soff.append(soff[-1] + len(t))
+        n += int(dmax[length]) + 1
+    return lbase, np.asarray(soff, dtype=np.uint32), "".join(strs).encode("ascii"), n
 
 
-def format_records(records: np.ndarray, idx_sorted: np.ndarray, lens_sorted: np.ndarray) -> str:
-    """Records -> the lines of amplicon_sorter.py:792-798: 'idxA:idxB:iden' or '...:reverse'."""
-    if records.shape[0] == 0:
+def format_records(records: np.ndarray, idx_sorted: np.ndarray, lens_sorted: np.ndarray, dcap: np.ndarray | None = None) -> str:
+    """Records -> the lines of amplicon_sorter.py:792-798: 'idxA:idxB:iden' or '...:reverse'.
+    Text assembly runs in the library's host-side C (asb_format_records); the iden strings are Python's."""
+    import ctypes as C
+
+    from . import _ffi
+
+    n = int(records.shape[0])
+    if n == 0:
         return ""
-    a = idx_sorted[records["i_pos"]]
-    b = idx_sorted[records["j_pos"]]
-    iden = _iden_strings(lens_sorted[records["j_pos"]], records["d"])
-    rev = records["reverse"].astype(bool)
-    parts = []
-    for x, y, s, r in zip(a.tolist(), b.tolist(), iden.tolist(), rev.tolist()):
-        parts.append(f"{x}:{y}:{s}:reverse\n" if r else f"{x}:{y}:{s}\n")
-    return "".join(parts)
+    records = np.ascontiguousarray(records)
+    idx32 = np.ascontiguousarray(idx_sorted, dtype=np.uint32)
+    len32 = np.ascontiguousarray(lens_sorted, dtype=np.uint32)
+    lbase, soff, sbuf, nstr = _iden_table(np.asarray(lens_sorted), records, dcap)
+    cap = n * (32 + 8) + 64
+    out = C.create_string_buffer(cap)
+    lib = _ffi.load()
+    k = lib.asb_format_records(records.ctypes.data, n, _ffi.ptr(idx32, C.c_uint32), _ffi.ptr(len32, C.c_uint32),
+                               _ffi.ptr(lbase, C.c_uint64), lbase.shape[0], _ffi.ptr(soff, C.c_uint32), nstr, sbuf,
+                               C.cast(out, C.c_void_p), cap)
+    if k < 0:
+        raise RuntimeError(f"asb_format_records failed ({k})")
+    return out.raw[:k].decode("ascii")
 
 
 class AllPairs:
@@ -97,6 +121,7 @@ class AllPairs:
         for k in ("fwd_survivors", "rc_survivors", "zone_checks", "word_updates", "screen_ms"):
             self.stats[k] += tot[k]
         self.stats["gpu_ms"] += tot["total_ms"]
+        self.last_dpass = dpass
         return perm, order, lens_sorted, recs, tl
 
     @staticmethod
@@ -160,7 +185,7 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
         d[:] = [d[i] for i in perm.tolist()]  # side effect (1): batch left length-sorted in place
         tl_total += tl
         if tl:
-            text = format_records(recs, rid_to_idx[order.astype(np.int64)], lens_sorted)
+            text = format_records(recs, rid_to_idx[order.astype(np.int64)], lens_sorted, getattr(ap, "last_dpass", None))
             with open(out_path, "a") as f:  # :803
                 f.write(text)
             wrote = True

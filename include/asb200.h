@@ -83,6 +83,14 @@ int asb_batch_step(asb_ctx *ctx, asb_step_info *info);
 /* Copies the records of the last step (info.n_records of them) to host memory. */
 int asb_batch_records(asb_ctx *ctx, asb_record *dst);
 
+/* Host-side helper (no GPU): assembles the tempfile text of amplicon_sorter.py:792-798,
+ * "idxA:idxB:iden[:reverse]\n" per record.  The iden strings are the caller's (the reference's own
+ * str(round(1 - d/L, 3)) evaluated in Python): string number lbase[L] + d lives at sbuf[soff[e] .. soff[e+1]).
+ * Returns the number of bytes written, or < 0 (-1 bad argument, -2 missing table entry, -3 out too small). */
+int64_t asb_format_records(const asb_record *recs, uint64_t n, const uint32_t *idx_sorted, const uint32_t *len_sorted,
+                           const uint64_t *lbase, uint32_t lbase_len, const uint32_t *soff, uint64_t n_strings,
+                           const char *sbuf, char *out, uint64_t cap);
+
 /* Same, into DEVICE memory on the context's device (for an NCCL gather of the per-GPU lists). */
 int asb_batch_records_dev(asb_ctx *ctx, asb_record *dev_dst);
 
