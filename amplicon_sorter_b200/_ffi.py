@@ -32,7 +32,8 @@ class EngineError(RuntimeError):
 _LIB = None
 
 SYMBOLS = ["asb_version", "asb_create", "asb_destroy", "asb_last_error", "asb_set_param", "asb_upload_reads",
-           "asb_batch_begin", "asb_batch_step", "asb_batch_records", "asb_distance_pairs", "asb_debug_read", "asb_batch_records_dev", "asb_int_peak", "asb_format_records"]
+           "asb_batch_begin", "asb_batch_step", "asb_batch_records", "asb_distance_pairs", "asb_debug_read", "asb_batch_records_dev", "asb_int_peak", "asb_format_records",
+           "asb_kmer_build", "asb_kmer_shared_pairs", "asb_kmer_shared_tile", "asb_threeway_pairs"]
 
 
 def lib_path() -> str:
@@ -66,6 +67,10 @@ def load():
     L.asb_int_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.asb_format_records.argtypes = [vp, C.c_uint64, u32p, u32p, u64p, C.c_uint32, u32p, C.c_uint64, C.c_char_p, vp, C.c_uint64]
     L.asb_format_records.restype = C.c_int64
+    L.asb_kmer_build.argtypes = [vp, C.c_int]
+    L.asb_kmer_shared_pairs.argtypes = [vp, u32p, u32p, C.c_uint64, u32p]
+    L.asb_kmer_shared_tile.argtypes = [vp, u32p, C.c_uint32, u32p, C.c_uint32, u32p]
+    L.asb_threeway_pairs.argtypes = [vp, u32p, u32p, C.c_uint64, u32p, u32p, C.c_uint32, C.POINTER(StepInfo)]
     L.asb_debug_read.argtypes = [vp, C.c_uint32, C.c_int, u8p, C.c_uint32]
     _LIB = L
     return L

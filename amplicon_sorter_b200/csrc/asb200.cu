@@ -132,11 +132,12 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         const uint64_t off = B.pos_off[job.j];
         tf = B.codes_f + off;
         tr = B.codes_r + off;
-        if (mode == M_EXACT) k = n;
-        else if ((uint32_t)n >= B.table_len) { atomicOr(&B.ctr[C_ERR], (unsigned long long)E_TABLE); ok = false; }
-        else if (mode == M_ZONE) k = (int)B.drev[n] - 1;
-        else { const uint32_t kk = B.dpass[n]; k = kk == 0xFFFFFFFFu ? -1 : (int)kk; }
-        if (n - m > k) ok = false;  // d >= n-m > k on either strand
+        const int L = n > m ? n : m;  // the cut-offs are indexed by the LONGER read (AS:233); all-pairs rows have n >= m
+        if (mode == M_EXACT) k = L;
+        else if ((uint32_t)L >= B.table_len) { atomicOr(&B.ctr[C_ERR], (unsigned long long)E_TABLE); ok = false; }
+        else if (mode == M_ZONE) k = (int)B.drev[L] - 1;
+        else { const uint32_t kk = B.dpass[L]; k = kk == 0xFFFFFFFFu ? -1 : (int)kk; }
+        if (abs(n - m) > k) ok = false;  // d >= |n-m| > k on either strand
     }
     const uint64_t key = ((uint64_t)row << 32) | job.j;
     if (m == 0) {  // empty query: d = n, no DP needed (never happens behind -min 300)
@@ -147,9 +148,10 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         return;
     }
     // ---- warp-uniform band geometry covering every participating lane
-    const int e = ok ? (k - (n - m)) >> 1 : 0;
-    const int Dmax = __reduce_max_sync(0xFFFFFFFFu, ok ? (n - m) + e : 0);
-    const int Emax = __reduce_max_sync(0xFFFFFFFFu, e);
+    // Ukkonen: a path of cost <= k stays on diagonals c - r in [-(e + max(m-n,0)), e + max(n-m,0)], e = (k-|n-m|)/2
+    const int e = ok ? (k - abs(n - m)) >> 1 : 0;
+    const int Dmax = __reduce_max_sync(0xFFFFFFFFu, ok ? e + max(n - m, 0) : 0);
+    const int Emax = __reduce_max_sync(0xFFFFFFFFu, ok ? e + max(m - n, 0) : 0);
     const int nmax = __reduce_max_sync(0xFFFFFFFFu, ok ? n : 0);
     const unsigned okm = __ballot_sync(0xFFFFFFFFu, ok);
     if (okm == 0u) {
@@ -319,6 +321,90 @@ __global__ void asb_encode(const uint8_t* __restrict__ ascii, const uint64_t* __
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// K2/K3: canonical k-mer presence bitsets and shared-k-mer counts.  NEW relative to the reference
+// (it has no k-mer stage): a validated side output / scheduling hint, never a decision.
+//   k-mer code = 2 bits per base (A,C,G,T = 0..3), canonical = min(code, code of the reverse
+//   complement); windows containing any other symbol are skipped; bit `canonical` of the read's
+//   4^k-bit set is set.  shared(i, j) = popcount(bits_i & bits_j).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) asb_kmer_build_kernel(const uint8_t* __restrict__ codes, const uint64_t* __restrict__ roff,
+                                                           const uint32_t* __restrict__ rlen, uint32_t n_reads,
+                                                           const uint8_t* __restrict__ base2 /*code -> 0..3 or 4*/, int k,
+                                                           uint32_t words, uint32_t* __restrict__ bits)
+{
+    extern __shared__ uint32_t sm[];
+    for (uint32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) sm[w] = 0u;
+        __syncthreads();
+        const uint8_t* q = codes + roff[r];
+        const int len = (int)rlen[r];
+        for (int p = threadIdx.x; p + k <= len; p += blockDim.x) {
+            uint32_t f = 0, v = 0;
+            bool ok = true;
+            for (int t = 0; t < k; ++t) {
+                const uint32_t b = base2[q[p + t]];
+                ok = ok && b < 4u;
+                f = (f << 2) | (b & 3u);
+                v |= (3u - (b & 3u)) << (2 * t);
+            }
+            if (ok) { const uint32_t c = f < v ? f : v; atomicOr(&sm[c >> 5], 1u << (c & 31)); }
+        }
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) bits[(uint64_t)r * words + w] = sm[w];
+        __syncthreads();
+    }
+}
+
+// one warp per pair: lanes stride over the bitset words, warp-level reduction
+__global__ void __launch_bounds__(256) asb_kmer_pairs_kernel(const uint32_t* __restrict__ bits, uint32_t words, const uint32_t* __restrict__ a,
+                                                           const uint32_t* __restrict__ b, uint64_t n, uint32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    for (uint64_t p = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5); p < n; p += (uint64_t)gridDim.x * 8) {
+        const uint32_t* x = bits + (uint64_t)a[p] * words;
+        const uint32_t* y = bits + (uint64_t)b[p] * words;
+        uint32_t acc = 0;
+        for (uint32_t w = lane; w < words; w += 32) acc += __popc(__ldg(x + w) & __ldg(y + w));
+        acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+        if (lane == 0) out[p] = acc;
+    }
+}
+
+// 32 x 32 tile of pairs per block: row and column bitsets staged through shared memory in chunks of
+// 128 words; warp w owns rows 4w..4w+3, lane = column; row words are broadcasts, column words are
+// read with an odd stride (conflict-free).
+constexpr int kKmerChunk = 128;
+__global__ void __launch_bounds__(256) asb_kmer_tile_kernel(const uint32_t* __restrict__ bits, uint32_t words, const uint32_t* __restrict__ rows,
+                                                          uint32_t nr, const uint32_t* __restrict__ cols, uint32_t nc, uint32_t* __restrict__ out)
+{
+    __shared__ uint32_t srow[32][kKmerChunk];
+    __shared__ uint32_t scol[32][kKmerChunk + 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    uint32_t acc[4] = {0, 0, 0, 0};
+    for (uint32_t wb = 0; wb < words; wb += kKmerChunk) {
+        const uint32_t cw = min((uint32_t)kKmerChunk, words - wb);
+        for (uint32_t x = threadIdx.x; x < 32 * cw; x += blockDim.x) {
+            const uint32_t i = x / cw, w = x % cw;
+            srow[i][w] = (r0 + i < nr) ? __ldg(bits + (uint64_t)rows[r0 + i] * words + wb + w) : 0u;
+            scol[i][w] = (c0 + i < nc) ? __ldg(bits + (uint64_t)cols[c0 + i] * words + wb + w) : 0u;
+        }
+        __syncthreads();
+        for (uint32_t w = 0; w < cw; ++w) {
+            const uint32_t cv = scol[lane][w];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += __popc(srow[wid * 4 + i][w] & cv);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t r = r0 + wid * 4 + i, c = c0 + lane;
+        if (r < nr && c < nc) out[(uint64_t)r * nc + c] = acc[i];
+    }
+}
+
 // INT32 ALU-pipe roofline probe: 16 independent dependency chains per thread.
 // which == 0: pure LOP3 (x = (x & a) ^ b);  which == 1: the Myers mix (7 LOP3 : 1 LEA/IADD3 : 2 SHF).
 __global__ void __launch_bounds__(256) asb_int_peak_kernel(uint32_t* __restrict__ sink, int iters, int which)
@@ -436,6 +522,8 @@ struct asb_ctx {
     uint64_t* rec_keys = nullptr; uint32_t* rec_vals = nullptr; uint64_t rec_n = 0;
     asb_record* h_stage = nullptr; size_t h_stage_n = 0;  // pinned staging
     uint32_t launches = 0;  // own kernels launched since the last step began
+    DevBuf<uint32_t> d_kbits; int kmer_k = 0; uint32_t kmer_words = 0;  // K2 bitsets
+    DevBuf<uint64_t> d_roff_all; DevBuf<uint32_t> d_rlen_all;
     DevBuf<asb_record> d_rec;
 };
 
@@ -473,7 +561,7 @@ int sort_list(asb_ctx* ctx, uint64_t* keys, uint32_t* vals, uint64_t n, uint64_t
 {
     *out_keys = keys; if (out_vals) *out_vals = vals;
     if (n <= 1) return ASB_OK;
-    const int end_bit = std::min(64, 32 + bits_for(ctx->n));
+    const int end_bit = std::min(64, 32 + bits_for(std::max(ctx->n, ctx->n_reads)));
     cub::DoubleBuffer<uint64_t> kb(keys, ctx->d_alt.p);
     size_t tmp = 0;
     if (vals) {
@@ -581,7 +669,7 @@ void asb_destroy(asb_ctx* ctx)
     ctx->d_cf.release(); ctx->d_cr.release(); ctx->d_pos_off.release(); ctx->d_pos_len.release(); ctx->d_hi.release();
     ctx->d_dpass.release(); ctx->d_drev.release(); ctx->d_grp.release(); ctx->d_F.release(); ctx->d_R.release(); ctx->d_Z.release();
     ctx->d_O.release(); ctx->d_alt.release(); ctx->d_Zv.release(); ctx->d_Ov.release(); ctx->d_altv.release(); ctx->d_ctr.release();
-    ctx->d_tmp.release(); ctx->d_rec.release();
+    ctx->d_tmp.release(); ctx->d_rec.release(); ctx->d_kbits.release(); ctx->d_roff_all.release(); ctx->d_rlen_all.release();
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -617,6 +705,7 @@ int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, u
         ctx->h_roff[r + 1] = ctx->h_roff[r] + (((uint64_t)len + 31) & ~31ull) + 64;  // 32-byte aligned regions + slack
     }
     ctx->max_len = max_len;
+    ctx->kmer_k = 0;
     const uint64_t total = ctx->h_roff[n_reads] + (((uint64_t)max_len + 31) & ~31ull) + 128;  // over-read slack for short lanes
     DevBuf<uint8_t> d_ascii; DevBuf<uint64_t> d_offs, d_roff; DevBuf<uint32_t> d_present; DevBuf<uint8_t> d_maps;
     struct Guard { DevBuf<uint8_t>&a; DevBuf<uint64_t>&b,&c; DevBuf<uint32_t>&d; DevBuf<uint8_t>&e; ~Guard(){a.release();b.release();c.release();d.release();e.release();} } guard{d_ascii, d_offs, d_roff, d_present, d_maps};
@@ -723,6 +812,42 @@ static int need_words(const asb_ctx* ctx, uint32_t p, const std::vector<uint32_t
     return (D + 31) / 32 + (E + 31) / 32 + 1;
 }
 
+// F -> R -> Z -> O: the list stages shared by the all-pairs step and the explicit pair-list entry point.
+// d_F holds nF unsorted keys; on return ctx->rec_keys/rec_vals/rec_n describe the sorted records.
+static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, uint64_t nF, asb_step_info* info)
+{
+    int rc;
+    info->fwd_survivors = nF;
+    uint64_t* keys; uint32_t* vals;
+    // F: full forward pass
+    rc = sort_list(ctx, ctx->d_F.p, nullptr, nF, &keys, nullptr); if (rc) return rc;
+    rc = run_list(ctx, B, M_FWD, cls, keys, nullptr, nF); if (rc) return rc;
+    rc = read_counters(ctx); if (rc) return rc;
+    const uint64_t nR = ctx->h_ctr[C_R];
+    info->rc_survivors = nR;
+    // R: full compl_reverse pass
+    rc = sort_list(ctx, ctx->d_R.p, nullptr, nR, &keys, nullptr); if (rc) return rc;
+    rc = run_list(ctx, B, M_RC, cls, keys, nullptr, nR); if (rc) return rc;
+    rc = read_counters(ctx); if (rc) return rc;
+    const uint64_t nZ = ctx->h_ctr[C_Z];
+    info->zone_checks = nZ;
+    // Z: exact forward decision at drev
+    rc = sort_list(ctx, ctx->d_Z.p, ctx->d_Zv.p, nZ, &keys, &vals); if (rc) return rc;
+    {
+        const int zbt = kClasses[zcls];
+        DevBatch BZ = B;
+        BZ.Wpad = odd_stride(wmax + (zbt > 0 ? zbt : 0) + 1);
+        rc = run_list(ctx, BZ, M_ZONE, zcls, keys, vals, nZ); if (rc) return rc;
+    }
+    rc = read_counters(ctx); if (rc) return rc;
+    const uint64_t nO = ctx->h_ctr[C_O];
+    rc = sort_list(ctx, ctx->d_O.p, ctx->d_Ov.p, nO, &ctx->rec_keys, &ctx->rec_vals); if (rc) return rc;
+    ctx->rec_n = nO;
+    info->n_records = nO;
+    info->word_updates = ctx->h_ctr[C_WORDS] * 32ull;
+    return ASB_OK;
+}
+
 int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
 {
     if (!ctx || !info) return ASB_E_ARG;
@@ -797,33 +922,8 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     rc = read_counters(ctx);
     if (rc) return rc;
-    const uint64_t nF = ctx->h_ctr[C_F];
-    info->fwd_survivors = nF;
-    uint64_t* keys; uint32_t* vals;
-    // F: full forward pass
-    rc = sort_list(ctx, ctx->d_F.p, nullptr, nF, &keys, nullptr); if (rc) return rc;
-    rc = run_list(ctx, B, M_FWD, cls, keys, nullptr, nF); if (rc) return rc;
-    rc = read_counters(ctx); if (rc) return rc;
-    const uint64_t nR = ctx->h_ctr[C_R];
-    info->rc_survivors = nR;
-    // R: full compl_reverse pass
-    rc = sort_list(ctx, ctx->d_R.p, nullptr, nR, &keys, nullptr); if (rc) return rc;
-    rc = run_list(ctx, B, M_RC, cls, keys, nullptr, nR); if (rc) return rc;
-    rc = read_counters(ctx); if (rc) return rc;
-    const uint64_t nZ = ctx->h_ctr[C_Z];
-    info->zone_checks = nZ;
-    // Z: exact forward decision at drev
-    rc = sort_list(ctx, ctx->d_Z.p, ctx->d_Zv.p, nZ, &keys, &vals); if (rc) return rc;
-    {
-        const int zbt = kClasses[zcls];
-        DevBatch BZ = B;
-        BZ.Wpad = odd_stride((int)wmax + (zbt > 0 ? zbt : 0) + 1);
-        rc = run_list(ctx, BZ, M_ZONE, zcls, keys, vals, nZ); if (rc) return rc;
-    }
-    rc = read_counters(ctx); if (rc) return rc;
-    const uint64_t nO = ctx->h_ctr[C_O];
-    rc = sort_list(ctx, ctx->d_O.p, ctx->d_Ov.p, nO, &ctx->rec_keys, &ctx->rec_vals); if (rc) return rc;
-    ctx->rec_n = nO;
+    rc = finish_lists(ctx, B, cls, zcls, (int)wmax, ctx->h_ctr[C_F], info);
+    if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
@@ -846,8 +946,6 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
         }
     }
     info->pairs = my_pairs;
-    info->n_records = nO;
-    info->word_updates = ctx->h_ctr[C_WORDS] * 32ull;
     info->row_begin = r0; info->row_end = r1;
     info->launches = ctx->launches;
     ctx->next_row = r1;
@@ -939,6 +1037,138 @@ int asb_int_peak(asb_ctx* ctx, int iters, double* lop3_tops, double* mix_tops)
     }
     *lop3_tops = out[0];
     *mix_tops = out[1];
+    return ASB_OK;
+}
+
+int asb_kmer_build(asb_ctx* ctx, int k)
+{
+    if (!ctx || k < 2 || k > 8) return fail(ctx, ASB_E_ARG, "k must be in 2..8");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t n = ctx->n_reads;
+    const uint32_t words = std::max<uint32_t>(1u, (1u << (2 * k)) / 32u);
+    CU(ctx->d_kbits.ensure((size_t)std::max<uint32_t>(n, 1) * words));
+    CU(ctx->d_roff_all.ensure((size_t)n + 1)); CU(ctx->d_rlen_all.ensure(std::max<uint32_t>(n, 1)));
+    uint8_t base2[256];
+    for (uint32_t c = 0; c <= ctx->sigma && c < 256; ++c) {
+        const uint8_t ch = ctx->code_to_ascii[c];
+        base2[c] = (c == ctx->sigma) ? 4 : (ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4);
+    }
+    DevBuf<uint8_t> d_b2;
+    struct Guard { DevBuf<uint8_t>& a; ~Guard() { a.release(); } } guard{d_b2};
+    CU(d_b2.ensure(256));
+    CU(cudaMemcpyAsync(d_b2.p, base2, 256, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        CU(cudaMemcpyAsync(ctx->d_roff_all.p, ctx->h_roff.data(), sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_rlen_all.p, ctx->h_rlen.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        asb_kmer_build_kernel<<<std::min<uint32_t>(n, (uint32_t)ctx->sm_count * 8), 256, words * sizeof(uint32_t), ctx->stream>>>(
+            ctx->d_cf.p, ctx->d_roff_all.p, ctx->d_rlen_all.p, n, d_b2.p, k, words, ctx->d_kbits.p);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->kmer_k = k; ctx->kmer_words = words;
+    return ASB_OK;
+}
+
+int asb_kmer_shared_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, uint64_t n, uint32_t* out)
+{
+    if (!ctx || (n && (!a || !b || !out))) return fail(ctx, ASB_E_ARG, "null argument");
+    if (!ctx->kmer_k) return fail(ctx, ASB_E_ARG, "asb_kmer_build has not been called for the uploaded reads");
+    if (n == 0) return ASB_OK;
+    for (uint64_t p = 0; p < n; ++p) if (a[p] >= ctx->n_reads || b[p] >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "pair %llu: bad read id", (unsigned long long)p);
+    CU(cudaSetDevice(ctx->device));
+    DevBuf<uint32_t> da, db, dout;
+    struct Guard { DevBuf<uint32_t>&a,&b,&c; ~Guard() { a.release(); b.release(); c.release(); } } guard{da, db, dout};
+    CU(da.ensure(n)); CU(db.ensure(n)); CU(dout.ensure(n));
+    CU(cudaMemcpyAsync(da.p, a, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(db.p, b, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 16);
+    asb_kmer_pairs_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_kbits.p, ctx->kmer_words, da.p, db.p, n, dout.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASB_OK;
+}
+
+int asb_kmer_shared_tile(asb_ctx* ctx, const uint32_t* rows, uint32_t nr, const uint32_t* cols, uint32_t nc, uint32_t* out)
+{
+    if (!ctx || ((nr && nc) && (!rows || !cols || !out))) return fail(ctx, ASB_E_ARG, "null argument");
+    if (!ctx->kmer_k) return fail(ctx, ASB_E_ARG, "asb_kmer_build has not been called for the uploaded reads");
+    if (nr == 0 || nc == 0) return ASB_OK;
+    for (uint32_t i = 0; i < nr; ++i) if (rows[i] >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "rows[%u]: bad read id", i);
+    for (uint32_t i = 0; i < nc; ++i) if (cols[i] >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "cols[%u]: bad read id", i);
+    CU(cudaSetDevice(ctx->device));
+    DevBuf<uint32_t> dr, dc, dout;
+    struct Guard { DevBuf<uint32_t>&a,&b,&c; ~Guard() { a.release(); b.release(); c.release(); } } guard{dr, dc, dout};
+    CU(dr.ensure(nr)); CU(dc.ensure(nc)); CU(dout.ensure((size_t)nr * nc));
+    CU(cudaMemcpyAsync(dr.p, rows, sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(dc.p, cols, sizeof(uint32_t) * nc, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((nc + 31) / 32, (nr + 31) / 32);
+    asb_kmer_tile_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_kbits.p, ctx->kmer_words, dr.p, nr, dc.p, nc, dout.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout.p, sizeof(uint32_t) * (size_t)nr * nc, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASB_OK;
+}
+
+// similarity()'s three-way rule on an explicit pair list (building block of similarity_species, AS:1692-1715).
+int asb_threeway_pairs(asb_ctx* ctx, const uint32_t* q, const uint32_t* t, uint64_t npairs, const uint32_t* dpass,
+                       const uint32_t* drev, uint32_t table_len, asb_step_info* info)
+{
+    if (!ctx || !info || (npairs && (!q || !t)) || !dpass || !drev) return fail(ctx, ASB_E_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    memset(info, 0, sizeof *info);
+    ctx->launches = 0;
+    ctx->in_batch = false;  // reuses the batch position arrays
+    ctx->rec_n = 0;
+    const uint32_t n = ctx->n_reads;
+    ctx->n = n;
+    if (npairs == 0) return ASB_OK;
+    std::vector<uint64_t> keys(npairs);
+    int need = 1, zneed = 1;
+    uint32_t wmax = 1;
+    for (uint64_t p = 0; p < npairs; ++p) {
+        if (q[p] >= n || t[p] >= n) return fail(ctx, ASB_E_ARG, "pair %llu references a read that was not uploaded", (unsigned long long)p);
+        const int m = (int)ctx->h_rlen[q[p]], nn = (int)ctx->h_rlen[t[p]];
+        const int L = std::max(m, nn), dl = std::abs(nn - m), W = (m + 31) / 32;
+        if ((uint32_t)L >= table_len) return fail(ctx, ASB_E_ARG, "read length %d >= table_len %u", L, table_len);
+        keys[p] = ((uint64_t)q[p] << 32) | t[p];
+        wmax = std::max<uint32_t>(wmax, (uint32_t)W);
+        for (int z = 0; z < 2; ++z) {
+            int k = z ? (int)drev[L] - 1 : (dpass[L] == 0xFFFFFFFFu ? -1 : (int)dpass[L]);
+            if (k < dl) continue;
+            const int e = (k - dl) / 2, D = e + std::max(nn - m, 0), E = e + std::max(m - nn, 0);
+            const int w = std::min((D + 31) / 32 + (E + 31) / 32 + 1, std::max(W, 1));
+            if (z) zneed = std::max(zneed, w); else need = std::max(need, w);
+        }
+    }
+    const int cls = class_for(need), zcls = class_for(zneed);
+    int rc = ensure_lists(ctx, std::max<uint64_t>(npairs, 32));
+    if (rc) return rc;
+    CU(ctx->d_pos_off.ensure(n)); CU(ctx->d_pos_len.ensure(n));
+    CU(ctx->d_dpass.ensure(table_len)); CU(ctx->d_drev.ensure(table_len));
+    CU(cudaMemcpyAsync(ctx->d_pos_off.p, ctx->h_roff.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_pos_len.p, ctx->h_rlen.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_dpass.p, dpass, sizeof(uint32_t) * table_len, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_drev.p, drev, sizeof(uint32_t) * table_len, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_F.p, keys.data(), sizeof(uint64_t) * npairs, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
+    DevBatch B;
+    memset(&B, 0, sizeof B);
+    B.codes_f = ctx->d_cf.p; B.codes_r = ctx->d_cr.p; B.pos_off = ctx->d_pos_off.p; B.pos_len = ctx->d_pos_len.p;
+    B.dpass = ctx->d_dpass.p; B.drev = ctx->d_drev.p; B.table_len = table_len; B.n = n; B.sigma = ctx->sigma;
+    B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
+    B.ctr = ctx->d_ctr.p; B.list_cap = ctx->list_cap;
+    const int bt = kClasses[cls];
+    B.Wpad = odd_stride((int)wmax + (bt > 0 ? bt : 0) + 1);
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    rc = finish_lists(ctx, B, cls, zcls, (int)wmax, npairs, info);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2])); info->total_ms = ms;
+    info->pairs = npairs;
+    info->launches = ctx->launches;
     return ASB_OK;
 }
 

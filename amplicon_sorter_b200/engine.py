@@ -114,6 +114,37 @@ class Engine:
         out = np.concatenate(recs) if recs else np.empty(0, dtype=RECORD)
         return out, tot
 
+    # -- three-way rule on an explicit pair list (similarity_species) ---------------------------------
+    def threeway_pairs(self, q, t, dpass, drev):
+        """Records (i_pos = q id, j_pos = t id, d, reverse) sorted by (q, t), plus the step info."""
+        q = np.ascontiguousarray(q, dtype=np.uint32)
+        t = np.ascontiguousarray(t, dtype=np.uint32)
+        dpass = np.ascontiguousarray(dpass, dtype=np.uint32)
+        drev = np.ascontiguousarray(drev, dtype=np.uint32)
+        info = StepInfo()
+        self._check(self._lib.asb_threeway_pairs(self._h, ptr(q, C.c_uint32), ptr(t, C.c_uint32), q.shape[0], ptr(dpass, C.c_uint32),
+                                                 ptr(drev, C.c_uint32), dpass.shape[0], C.byref(info)))
+        return self.batch_records(info.n_records), info.as_dict()
+
+    # -- k-mer side output (new; no reference counterpart) --------------------------------------------
+    def kmer_build(self, k: int = 6):
+        self._check(self._lib.asb_kmer_build(self._h, int(k)))
+
+    def kmer_shared_pairs(self, a, b) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        out = np.empty(a.shape[0], dtype=np.uint32)
+        self._check(self._lib.asb_kmer_shared_pairs(self._h, ptr(a, C.c_uint32), ptr(b, C.c_uint32), a.shape[0], ptr(out, C.c_uint32)))
+        return out
+
+    def kmer_shared_tile(self, rows, cols) -> np.ndarray:
+        rows = np.ascontiguousarray(rows, dtype=np.uint32)
+        cols = np.ascontiguousarray(cols, dtype=np.uint32)
+        out = np.empty((rows.shape[0], cols.shape[0]), dtype=np.uint32)
+        self._check(self._lib.asb_kmer_shared_tile(self._h, ptr(rows, C.c_uint32), rows.shape[0], ptr(cols, C.c_uint32),
+                                                   cols.shape[0], ptr(out, C.c_uint32)))
+        return out
+
     # -- distance() on explicit pairs --------------------------------------------------------------
     def distance_pairs(self, a, b, strand=None) -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint32)

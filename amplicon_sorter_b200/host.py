@@ -200,3 +200,66 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
             rf.write("No reads to compare, exiting...")
         raise NoReadsToCompare()
     return None
+
+
+def process_consensuslist(indexes, grouplist, group_filename, *, args, comparelist2, similar, engine):
+    """Drop-in for ``process_consensuslist(indexes, grouplist, group_filename)`` (amplicon_sorter.py:1627-1690)
+    together with its worker ``similarity_species`` (:1692-1715): reads not yet in a sub-group x the
+    consensus of every sub-group, same three-way rule as ``similarity`` with the cut ``similar - 0.01``
+    evaluated in the reference's float arithmetic (:1700), lines ``read_idx:group_no:iden`` in the
+    -np 1 order (read, then group) appended to ``<group>.tmp``.
+
+    Quirks kept: the two-sided 5 % window (:1663); the cap of 100 spool files x 2,000,000 comparisons,
+    checked after each read (:1675-1676); nothing at all is compared when the LAST spool chunk is empty
+    (:1687 -- a comparison count that is an exact multiple of 2,000,000, including zero).
+    `args`, `comparelist2` and `similar` are the reference's module globals at call time."""
+    outputfolder = args.outputfolder
+    group_tempfile = os.path.join(outputfolder, group_filename).replace(".group", ".tmp")
+    for x in [group_tempfile] + glob.glob(os.path.join(outputfolder, "*.todo")):
+        try:
+            os.remove(x)
+        except FileNotFoundError:
+            pass
+    indexes2 = indexes.copy()
+    for x in grouplist:
+        for y in x:
+            if y.isdigit():
+                indexes2.discard(y)
+    consensuslist = [[x, y[-1]] for x, y in enumerate(grouplist)]
+    comparelist4 = [i for i in comparelist2 if str(i[3]) in indexes2]
+    rl = np.fromiter((len(r[1]) for r in comparelist4), dtype=np.int64, count=len(comparelist4))
+    cl = np.fromiter((len(c[1]) for c in consensuslist), dtype=np.int64, count=len(consensuslist))
+    # window :1663  `len(A1)*1.05 < len(A2) or len(A2)*1.05 < len(A1)` -> skip   (float64, as in Python)
+    keep = ~((rl[:, None].astype(np.float64) * 1.05 < cl[None, :]) | (cl[None, :].astype(np.float64) * 1.05 < rl[:, None])) \
+        if rl.size and cl.size else np.zeros((rl.size, cl.size), dtype=bool)
+    per_read = keep.sum(axis=1)
+    cum = np.cumsum(per_read)
+    stop = np.nonzero(cum // 2000000 >= 100)[0]  # :1675 `if k == 100: break`, tested after each read
+    n_reads_used = int(stop[0]) + 1 if stop.size else rl.size
+    keep[n_reads_used:, :] = False
+    l_total = int(cum[n_reads_used - 1]) if n_reads_used else 0
+    print(group_filename + "----> " + str(l_total) + " comparisons to calculate")
+    if l_total % 2000000 == 0:  # :1687 `if len(todolist) > 0:` -- the last chunk is empty, nothing runs
+        return None
+    xs, ys = np.nonzero(keep)  # enumeration order: read, then group
+    seqs = [r[1] for r in comparelist4[:n_reads_used]] + [c[1] for c in consensuslist]
+    lens = np.concatenate([rl[:n_reads_used], cl])
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offs[1:])
+    buf = np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8)
+    engine.upload_reads(buf, offs)
+    cut = similar - 0.01  # :1700, raw float (0.94 - 0.01 = 0.9299999999999999)
+    dpass, drev = thresholds.tables(cut, int(lens.max()) + 1)
+    q = (ys + n_reads_used).astype(np.uint32)  # the consensus is the DP query: many reads share its match masks
+    t = xs.astype(np.uint32)
+    recs, _ = engine.threeway_pairs(q, t, dpass, drev)
+    order = np.lexsort((recs["i_pos"], recs["j_pos"]))  # back to (read, group) order
+    lines = []
+    for r in recs[order].tolist():
+        qi, ti, d, _rev = r
+        y, x = qi - n_reads_used, ti
+        iden = round(1 - d / max(int(rl[x]), int(cl[y])), 3)  # :233 len(longer)
+        lines.append(str(comparelist4[x][3]) + ":" + str(consensuslist[y][0]) + ":" + str(iden) + "\n")
+    with open(os.path.join(outputfolder, group_tempfile), "a") as f:  # :1709
+        f.writelines(lines)
+    return None

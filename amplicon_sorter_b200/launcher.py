@@ -59,6 +59,23 @@ def install_gpu_stage(ns, device: int = 0, stats: dict | None = None, engine_fac
 
     process_list.__doc__ = host.process_list.__doc__
     ns["process_list"] = process_list
+
+    # "next" row of the scope table: reads x group consensuses (:1627-1715).  One engine is kept for the
+    # ~30 calls per gene group; opt out with ASB200_STAGES=process_list.
+    if "process_consensuslist" in os.environ.get("ASB200_STAGES", "process_list,process_consensuslist"):
+        keep = {}
+
+        def process_consensuslist(indexes, grouplist, group_filename):
+            eng = engine_factory() if engine_factory else keep.get("engine")
+            if eng is None:
+                from .engine import Engine
+
+                eng = keep["engine"] = Engine(device)
+            return host.process_consensuslist(indexes, grouplist, group_filename, args=ns["args"],
+                                              comparelist2=ns["comparelist2"], similar=ns["similar"], engine=eng)
+
+        process_consensuslist.__doc__ = host.process_consensuslist.__doc__
+        ns["process_consensuslist"] = process_consensuslist
     ns["check_version"] = lambda version: None  # :39-72 fetches GitHub and may sleep 10 s; not part of the path
 
 

@@ -98,11 +98,28 @@ int asb_batch_records_dev(asb_ctx *ctx, asb_record *dev_dst);
  * LOP3 and the instruction mix of the Myers word-update -- the roofline the path is bound by. */
 int asb_int_peak(asb_ctx *ctx, int iters, double *lop3_tops, double *mix_tops);
 
+/* Replaces similarity_species' per-pair rule (:1692-1715, same three-way rule as :790-798) on an explicit
+ * list of uploaded read ids.  q[p] is used as the DP query and t[p] as the target (any length order:
+ * the distance is symmetric; the cut-offs are indexed by the longer of the two, :233).  Records come
+ * back through asb_batch_records[_dev] sorted by (q, t): i_pos = q, j_pos = t, d, reverse. */
+int asb_threeway_pairs(asb_ctx *ctx, const uint32_t *q, const uint32_t *t, uint64_t npairs, const uint32_t *dpass,
+                       const uint32_t *drev, uint32_t table_len, asb_step_info *info);
+
 /* Replaces distance(X1, X2, mode) (:224-234) on an explicit pair list of uploaded read ids:
  * out_d[p] = exact edit distance, NW (mode 0) between a[p] and b[p] (shorter one is the query);
  * strand 1 compares against compl_reverse of the longer read. */
 int asb_distance_pairs(asb_ctx *ctx, const uint32_t *a, const uint32_t *b, const uint8_t *strand,
                        uint64_t npairs, int mode, int32_t *out_d);
+
+/* NEW relative to the reference (it has no k-mer stage): canonical k-mer presence
+ * bitsets of the uploaded reads (k in 2..8; A,C,G,T only, windows with other symbols skipped) and
+ * shared-k-mer counts popcount(bits_a & bits_b).  A validated side output and scheduling hint; it
+ * never takes a pass/fail decision.  Checked against oracle/asref.c::asref_kmer_*. */
+int asb_kmer_build(asb_ctx *ctx, int k);
+int asb_kmer_shared_pairs(asb_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n, uint32_t *out);
+/* out[r * nc + c] for every (rows[r], cols[c]); tiled 32 x 32 through shared memory */
+int asb_kmer_shared_tile(asb_ctx *ctx, const uint32_t *rows, uint32_t nr, const uint32_t *cols, uint32_t nc,
+                         uint32_t *out);
 
 /* Introspection for tests: symbol codes of read r (forward or compl_reverse) as the device holds
  * them, translated back to ASCII. */

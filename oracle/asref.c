@@ -475,6 +475,44 @@ int64_t asref_distance_pairs(const uint8_t *seqs, const uint64_t *offs, const ui
 }
 
 /* ------------------------------------------------------------------------------------------
+ * k-mer side output (NOT in the reference -- parity unpinned; this restates include/asb200.h's own
+ * definition so the CUDA kernels have an independent checker): canonical k-mer presence bitset of
+ * one read (A,C,G,T = 0..3; canonical = min(code, reverse-complement code); windows with any other
+ * byte skipped) and the shared count popcount(bits_a & bits_b).
+ * ------------------------------------------------------------------------------------------ */
+static int base2_of(uint8_t c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4; }
+
+void asref_kmer_bitset(const uint8_t *s, int32_t len, int k, uint32_t *bits /* 4^k/32 words, >= 1 */)
+{
+    uint32_t words = (1u << (2 * k)) / 32u;
+    if (words < 1) words = 1;
+    memset(bits, 0, sizeof(uint32_t) * words);
+    for (int32_t p = 0; p + k <= len; p++) {
+        uint32_t f = 0, v = 0;
+        int ok = 1;
+        for (int t = 0; t < k; t++) {
+            int b = base2_of(s[p + t]);
+            if (b > 3) { ok = 0; break; }
+            f = (f << 2) | (uint32_t)b;
+            v |= (uint32_t)(3 - b) << (2 * t);
+        }
+        if (ok) { uint32_t c = f < v ? f : v; bits[c >> 5] |= 1u << (c & 31); }
+    }
+}
+
+uint32_t asref_kmer_shared(const uint8_t *a, int32_t la, const uint8_t *b, int32_t lb, int k)
+{
+    uint32_t words = (1u << (2 * k)) / 32u;
+    if (words < 1) words = 1;
+    uint32_t *x = (uint32_t *)malloc(sizeof(uint32_t) * 2 * words), *y = x + words, acc = 0;
+    asref_kmer_bitset(a, la, k, x);
+    asref_kmer_bitset(b, lb, k, y);
+    for (uint32_t w = 0; w < words; w++) acc += (uint32_t)__builtin_popcount(x[w] & y[w]);
+    free(x);
+    return acc;
+}
+
+/* ------------------------------------------------------------------------------------------
  * NW alignment path for the edlib shim's task='path' (create_alignment AS:332).  Standard CIGAR
  * with M/I/D: I = symbol present in the query only, D = symbol present in the target only
  * (SURVEY Appendix A).  eq[256*256] is the symmetric equality table (additionalEqualities).

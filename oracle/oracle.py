@@ -49,6 +49,8 @@ def lib():
         L.asref_format_lines.restype = C.c_int64
         L.asref_distance_pairs.argtypes = [u8p, u64p, u32p, u32p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int]
         L.asref_distance_pairs.restype = C.c_int64
+        L.asref_kmer_shared.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_int]
+        L.asref_kmer_shared.restype = C.c_uint32
         L.asref_nw_path.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_char_p, i32p]
         L.asref_nw_path.restype = C.c_int64
         _LIB = L
@@ -134,6 +136,10 @@ def distance_pairs(seqs, offs, a, b, algo="myers", mode="NW", nthreads=0) -> np.
     return out
 
 
+def kmer_shared(a: bytes, b: bytes, k: int) -> int:
+    return lib().asref_kmer_shared(a, len(a), b, len(b), k)
+
+
 def nw_path(q: bytes, t: bytes, eq_table: bytes):
     ops = C.create_string_buffer(len(q) + len(t) + 1)
     d = C.c_int32()
@@ -187,4 +193,40 @@ def py_process_list(batches, similar_genes=80.0):
                     iden_ = py_distance(A1[1], py_compl_reverse(A2[1]))
                     if iden_ >= similarg:
                         lines.append(str(A1[3]) + ":" + str(A2[3]) + ":" + str(iden_) + ":reverse")
+    return lines
+
+
+def py_process_consensuslist(indexes, grouplist, comparelist2, similar):
+    """process_consensuslist AS:1627-1690 + similarity_species AS:1692-1715 at -np 1 -> list of lines
+    (None when the reference would not run the comparison at all: empty last spool chunk, AS:1687)."""
+    indexes2 = indexes.copy()
+    for x in grouplist:
+        for y in x:
+            if y.isdigit():
+                indexes2.discard(y)
+    consensuslist = [[x, y[-1]] for x, y in enumerate(grouplist)]
+    comparelist4 = [i for i in comparelist2 if str(i[3]) in indexes2]
+    todo, k, chunk = [], 0, 0
+    for A1 in comparelist4:
+        for A2 in consensuslist:
+            if len(A1[1]) * 1.05 < len(A2[1]) or len(A2[1]) * 1.05 < len(A1[1]):
+                continue
+            todo.append([A1, A2])
+            chunk += 1
+            if chunk == 2000000:
+                chunk = 0
+                k += 1
+        if k == 100:
+            break
+    if chunk == 0:
+        return None
+    lines = []
+    for A1, A2 in todo:
+        iden = py_distance(A1[1], A2[1])
+        if iden >= similar - 0.01:
+            lines.append(str(A1[3]) + ":" + str(A2[0]) + ":" + str(iden))
+        elif iden < 0.5:
+            iden = py_distance(A1[1], py_compl_reverse(A2[1]))
+            if iden >= similar - 0.01:
+                lines.append(str(A1[3]) + ":" + str(A2[0]) + ":" + str(iden))
     return lines

@@ -52,6 +52,13 @@ def main():
 
         ns["process_list"] = process_list
 
+        def process_consensuslist(indexes, grouplist, group_filename):
+            return host.process_consensuslist(indexes, grouplist, group_filename, args=ns["args"],
+                                              comparelist2=ns["comparelist2"], similar=ns["similar"], engine=OracleEngine())
+
+        if "process_consensuslist" in os.environ.get("ASB200_STAGES", "process_list,process_consensuslist"):
+            ns["process_consensuslist"] = process_consensuslist
+
     inner_pl = ns["process_list"]
     inner_sg = ns["sort_groups"]
 

@@ -57,5 +57,27 @@ class OracleEngine:
                "word_updates": 0, "screen_ms": 0.0, "total_ms": 0.0, "steps": 1}
         return recs, tot
 
+    def threeway_pairs(self, q, t, dpass, drev):
+        q = np.asarray(q, dtype=np.uint32)
+        t = np.asarray(t, dtype=np.uint32)
+        lens = (self.offs[1:] - self.offs[:-1]).astype(np.int64)
+        d = oracle.distance_pairs(self.buf, self.offs, q, t)
+        L = np.maximum(lens[q], lens[t])
+        rows = []
+        for p in range(q.shape[0]):
+            if d[p] <= int(dpass[L[p]]):
+                rows.append((int(q[p]), int(t[p]), int(d[p]), 0))
+            elif d[p] >= int(drev[L[p]]):
+                x = self.buf[self.offs[q[p]]:self.offs[q[p] + 1]].tobytes()
+                y = self.buf[self.offs[t[p]]:self.offs[t[p] + 1]].tobytes()
+                if len(x) > len(y):
+                    x, y = y, x
+                dr = oracle.nw(x, oracle.compl_reverse(y), "myers")  # compl_reverse of either side gives the same distance
+                if dr <= int(dpass[L[p]]):
+                    rows.append((int(q[p]), int(t[p]), dr, 1))
+        rows.sort()
+        recs = np.array(rows, dtype=RECORD) if rows else np.empty(0, dtype=RECORD)
+        return recs, {"pairs": int(q.shape[0]), "n_records": len(rows)}
+
     def close(self):
         self.closed = True

@@ -187,3 +187,29 @@ def test_dead_zone_edges(engine):
     util.assert_same_records(got, want)
     assert tot["zone_checks"] >= sum(found.values())
     assert (want["reverse"] == 1).sum() >= 2  # some dead-zone pairs emit, some are suppressed
+
+
+@pytest.mark.parametrize("k", [2, 5, 6, 8])
+def test_kmer_side_output_matches_its_oracle(engine, k):
+    """K2/K3 have no reference counterpart: checked against oracle/asref.c's restatement."""
+    rng = np.random.default_rng(50 + k)
+    reads = util.random_reads(rng, 70, 40, 400, families=4, err=0.08) + util.random_reads(rng, 10, 1, 30, alphabet=b"ACGTN")
+    reads += [b"A", b"ACGT" * 50, oracle.compl_reverse(reads[0])]
+    buf, offs = synth.pack_reads(reads)
+    engine.upload_reads(buf, offs)
+    engine.kmer_build(k)
+    n = len(reads)
+    a = rng.integers(0, n, 300).astype(np.uint32)
+    b = rng.integers(0, n, 300).astype(np.uint32)
+    got = engine.kmer_shared_pairs(a, b)
+    want = np.array([oracle.kmer_shared(reads[x], reads[y], k) for x, y in zip(a, b)], dtype=np.uint32)
+    assert np.array_equal(got, want)
+    rows = rng.permutation(n)[:45].astype(np.uint32)
+    cols = rng.permutation(n)[:70].astype(np.uint32)
+    tile = engine.kmer_shared_tile(rows, cols)
+    for r in range(0, 45, 4):
+        for c in range(0, 70, 5):
+            assert tile[r, c] == oracle.kmer_shared(reads[rows[r]], reads[cols[c]], k)
+    # same template, opposite strands share almost everything; unrelated reads share little (k=8)
+    if k == 8:
+        assert engine.kmer_shared_pairs([0], [n - 1])[0] == oracle.kmer_shared(reads[0], reads[0], k)

@@ -113,3 +113,13 @@ def test_synth_configs_are_deterministic():
     assert a == b and la == lb and len(a) == 50
     r5, _, args5 = synth.make_config(5, scale=0.004)
     assert len(r5) == 400 and args5[0] == "-a"
+
+
+def test_kmer_oracle_small_cases():
+    # AAAA: one 2-mer AA, canonical min(AA=0, TT=15) = 0; TTTT hits the same canonical k-mer
+    assert oracle.kmer_shared(b"AAAA", b"TTTT", 2) == 1
+    assert oracle.kmer_shared(b"AAAA", b"CCCC", 2) == 0
+    assert oracle.kmer_shared(b"ACGT", b"ACGT", 2) == 2  # AC/GT -> same canonical, CG (palindrome): 2 distinct
+    assert oracle.kmer_shared(b"ACNGT", b"ACGT", 2) == 1  # the windows over N are skipped
+    s = b"ACGTTGCAAGGCTTAACCGGTT"
+    assert oracle.kmer_shared(s, oracle.compl_reverse(s), 5) == oracle.kmer_shared(s, s, 5)  # strand-independent
