@@ -81,4 +81,4 @@ def test_threeway_pairs_any_length_order(engine):
         fe.upload_reads(buf, offs)
         want, _ = fe.threeway_pairs(q, t, dpass, drev)
         util.assert_same_records(got, want)
-        assert info["pairs"] == q.shape[0] and len(want) > 50
+        assert info["pairs"] == q.shape[0] and len(want) > 10
