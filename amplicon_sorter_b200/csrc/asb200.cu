@@ -61,6 +61,7 @@ struct DevBatch {
     // list task space
     const uint64_t* list; const uint32_t* list_val; uint64_t list_n;
     const uint8_t* ex_strand; int32_t* ex_out;  // M_EXACT
+    int ex_hw;                                  // M_EXACT: 1 = edlib HW (infix) distance
 };
 
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
@@ -144,7 +145,7 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         const bool pass = ok && n <= k;
         if (mode == M_SCREEN || mode == M_FWD) warp_push(pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, ((uint32_t)n << 1), &B.ctr[C_ERR]);
         if (mode == M_ZONE) warp_push(job.valid && !pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, (job.zval << 1) | 1u, &B.ctr[C_ERR]);
-        if (mode == M_EXACT && job.valid) B.ex_out[job.entry] = n;
+        if (mode == M_EXACT && job.valid) B.ex_out[job.entry] = B.ex_hw ? 0 : n;
         return;
     }
     // ---- warp-uniform band geometry covering every participating lane
@@ -169,6 +170,13 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         return;
     }
     const int full_cols = (nmax + 31) & ~31;
+    if (BT == 0 && mode == M_EXACT && B.ex_hw) {  // infix distance: full matrix, free top row
+        build_peq(peq, B, q, m, W);
+        const uint8_t* t = job.strand ? tr : tf;
+        const int best = hw_pass(peq, B.Wpad, W, m, t, n, nmax, cols_acc);
+        if (job.valid) B.ex_out[job.entry] = best;
+        return;
+    }
     g.ncols = full_cols;
     int push = 0;
     if (mode == M_SCREEN) {
@@ -1175,7 +1183,7 @@ int asb_threeway_pairs(asb_ctx* ctx, const uint32_t* q, const uint32_t* t, uint6
 int asb_distance_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const uint8_t* strand, uint64_t npairs, int mode, int32_t* out_d)
 {
     if (!ctx || (npairs && (!a || !b || !out_d))) return fail(ctx, ASB_E_ARG, "null argument");
-    if (mode != 0) return fail(ctx, ASB_E_ARG, "only mode 0 (NW) is implemented");
+    if (mode != 0 && mode != 1) return fail(ctx, ASB_E_ARG, "mode must be 0 (NW) or 1 (HW)");
     if (npairs == 0) return ASB_OK;
     CU(cudaSetDevice(ctx->device));
     ctx->in_batch = false;  // reuses the batch position arrays
@@ -1205,7 +1213,7 @@ int asb_distance_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const
     DevBatch B;
     memset(&B, 0, sizeof B);
     B.codes_f = ctx->d_cf.p; B.codes_r = ctx->d_cr.p; B.pos_off = ctx->d_pos_off.p; B.pos_len = ctx->d_pos_len.p;
-    B.n = n; B.sigma = ctx->sigma; B.ctr = ctx->d_ctr.p; B.ex_strand = d_st.p; B.ex_out = d_out.p;
+    B.n = n; B.sigma = ctx->sigma; B.ctr = ctx->d_ctr.p; B.ex_strand = d_st.p; B.ex_out = d_out.p; B.ex_hw = mode;
     B.Wpad = odd_stride((int)wmax + 1);
     int rc = run_list(ctx, B, M_EXACT, kNumClasses - 1, d_keys.p, nullptr, npairs);
     if (rc) return rc;

@@ -264,4 +264,29 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
     if (alive) status = PASS_SURVIVOR;
 }
 
+// edlib's HW ("infix") mode, used by iden_consensus (amplicon_sorter.py:1145-1147): min over all
+// substrings T' of the target of Levenshtein(query, T').  Same recurrence with a free top row
+// (D[0][c] = 0, hin = 0 above word 0) and the answer min_c D[m][c].  No band: the consensus x
+// consensus stage is G^2 pairs of ~1 kb, five orders of magnitude below the read stage, so the
+// full matrix over W = ceil(m/32) words (state in local memory) is kept simple and exact.
+__device__ __forceinline__ int hw_pass(const uint32_t* __restrict__ peq, const int Wpad, const int W, const int m,
+                                       const uint8_t* __restrict__ tgt, const int n, const int ncols, unsigned long long& work)
+{
+    uint32_t Pv[kMaxDynWords], Mv[kMaxDynWords];
+    for (int t = 0; t < W; ++t) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; }
+    const int bm = (m - 1) & 31;
+    int sm = m, best = m;  // D[m][0] = m
+    for (int c = 0; c < ncols; ++c) {
+        const uint32_t sym = tgt[c];
+        const uint32_t* __restrict__ row = peq + sym * Wpad;
+        uint32_t php = 0u, mhp = 0u, hmb = 0u;  // hin = 0: every target position may start the match
+        for (int t = 0; t < W; ++t) ASB_WORD_UPDATE(row[t], Pv[t], Mv[t], php, mhp, hmb)
+        // php/mhp hold Ph/Mh of the last word (the one with row m): its bit bm is D[m][c+1] - D[m][c]
+        sm += (int)((php >> bm) & 1u) - (int)((mhp >> bm) & 1u);
+        if (c < n && sm < best) best = sm;
+    }
+    work += (unsigned long long)ncols * (unsigned)W;
+    return best;
+}
+
 }  // namespace asb

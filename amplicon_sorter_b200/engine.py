@@ -146,7 +146,7 @@ class Engine:
         return out
 
     # -- distance() on explicit pairs --------------------------------------------------------------
-    def distance_pairs(self, a, b, strand=None) -> np.ndarray:
+    def distance_pairs(self, a, b, strand=None, mode: str = "NW") -> np.ndarray:
         a = np.ascontiguousarray(a, dtype=np.uint32)
         b = np.ascontiguousarray(b, dtype=np.uint32)
         out = np.empty(a.shape[0], dtype=np.int32)
@@ -154,6 +154,6 @@ class Engine:
         if strand is not None:
             strand = np.ascontiguousarray(strand, dtype=np.uint8)
             sp = ptr(strand, C.c_uint8)
-        self._check(self._lib.asb_distance_pairs(self._h, ptr(a, C.c_uint32), ptr(b, C.c_uint32), sp, a.shape[0], 0,
+        self._check(self._lib.asb_distance_pairs(self._h, ptr(a, C.c_uint32), ptr(b, C.c_uint32), sp, a.shape[0], 1 if mode == "HW" else 0,
                                                  ptr(out, C.c_int32)))
         return out

@@ -263,3 +263,46 @@ def process_consensuslist(indexes, grouplist, group_filename, *, args, compareli
     with open(os.path.join(outputfolder, group_tempfile), "a") as f:  # :1709
         f.writelines(lines)
     return None
+
+
+def iden_consensus_files(outputfolder, consensus_tempfile, stringx, *, engine):
+    """Drop-in for ``do_parallel(..., iden_consensus, ...)`` (amplicon_sorter.py:1160-1203 driving the worker
+    ``iden_consensus`` :1139-1158): every spooled ``[A1, A2, y, z]`` gets the edlib-HW (infix) identity on
+    both strands, the larger of the two is kept, and ``y,z,iden`` is appended to the consensus tempfile
+    if it is >= 0.60 (:1151) -- in the -np 1 order (spool files by mtime, entries in list order)."""
+    import pickle
+
+    names = [n for n in os.listdir(outputfolder) if n.endswith(".todo")]
+    names.sort(key=lambda x: os.path.getmtime(os.path.join(outputfolder, x)))
+    for name in names:
+        print(stringx + name)
+        with open(os.path.join(outputfolder, name), "rb") as rf:
+            todolist = pickle.load(rf)
+        os.remove(os.path.join(outputfolder, name))
+        lines = []
+        if todolist:
+            ids: dict = {}
+            seqs: list = []
+            a = np.empty(len(todolist), dtype=np.uint32)
+            b = np.empty(len(todolist), dtype=np.uint32)
+            for p, (A1, A2, _y, _z) in enumerate(todolist):
+                for arr, s in ((a, A1), (b, A2)):
+                    k = ids.get(s)
+                    if k is None:
+                        k = ids[s] = len(seqs)
+                        seqs.append(s)
+                    arr[p] = k
+            lens = np.fromiter((len(x) for x in seqs), dtype=np.uint64, count=len(seqs))
+            offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+            np.cumsum(lens, out=offs[1:])
+            engine.upload_reads(np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8), offs)
+            n = len(todolist)
+            strand = np.concatenate([np.zeros(n, np.uint8), np.ones(n, np.uint8)])
+            d = engine.distance_pairs(np.concatenate([a, a]), np.concatenate([b, b]), strand, mode="HW")
+            for p, (A1, A2, y, z) in enumerate(todolist):
+                L = max(len(A1), len(A2))
+                iden = max(round(1 - int(d[p]) / L, 3), round(1 - int(d[n + p]) / L, 3))  # :1145-1150
+                if iden >= 0.60:  # :1151
+                    lines.append(str(y) + "," + str(z) + "," + str(iden) + "\n")
+        with open(os.path.join(outputfolder, consensus_tempfile), "a") as f:  # :1154 (created even when empty)
+            f.writelines(lines)

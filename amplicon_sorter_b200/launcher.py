@@ -76,6 +76,22 @@ def install_gpu_stage(ns, device: int = 0, stats: dict | None = None, engine_fac
 
         process_consensuslist.__doc__ = host.process_consensuslist.__doc__
         ns["process_consensuslist"] = process_consensuslist
+
+        # consensus x consensus (:1139-1158): intercept the worker-pool dispatch for that one worker
+        if "iden_consensus" in os.environ.get("ASB200_STAGES", "iden_consensus"):
+            original_do_parallel = ns["do_parallel"]
+
+            def do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename):
+                if getattr(worker, "__name__", "") != "iden_consensus":
+                    return original_do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename)
+                eng = engine_factory() if engine_factory else keep.get("engine")
+                if eng is None:
+                    from .engine import Engine
+
+                    eng = keep["engine"] = Engine(device)
+                return host.iden_consensus_files(outputfolder, consensus_tempfile, stringx, engine=eng)
+
+            ns["do_parallel"] = do_parallel
     ns["check_version"] = lambda version: None  # :39-72 fetches GitHub and may sleep 10 s; not part of the path
 
 

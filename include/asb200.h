@@ -106,8 +106,9 @@ int asb_threeway_pairs(asb_ctx *ctx, const uint32_t *q, const uint32_t *t, uint6
                        const uint32_t *drev, uint32_t table_len, asb_step_info *info);
 
 /* Replaces distance(X1, X2, mode) (:224-234) on an explicit pair list of uploaded read ids:
- * out_d[p] = exact edit distance, NW (mode 0) between a[p] and b[p] (shorter one is the query);
- * strand 1 compares against compl_reverse of the longer read. */
+ * out_d[p] = exact edit distance between a[p] and b[p], the shorter one being the query (:225-230):
+ * mode 0 = edlib NW (global), mode 1 = edlib HW (infix: best match of the query inside the target,
+ * as iden_consensus uses it at :1145-1147).  strand[p] = 1 compares against compl_reverse. */
 int asb_distance_pairs(asb_ctx *ctx, const uint32_t *a, const uint32_t *b, const uint8_t *strand,
                        uint64_t npairs, int mode, int32_t *out_d);
 

@@ -230,3 +230,31 @@ def py_process_consensuslist(indexes, grouplist, comparelist2, similar):
             if iden >= similar - 0.01:
                 lines.append(str(A1[3]) + ":" + str(A2[0]) + ":" + str(iden))
     return lines
+
+
+def py_hw(q: str, t: str) -> int:
+    """edlib HW by definition: min over substrings of t (free leading/trailing target gaps)."""
+    prev = list(range(len(q) + 1))
+    best = prev[-1]
+    for cb in t:
+        cur = [0]
+        for i, ca in enumerate(q, 1):
+            cur.append(min(prev[i] + 1, cur[i - 1] + 1, prev[i - 1] + (ca != cb)))
+        prev = cur
+        best = min(best, prev[-1])
+    return best
+
+
+def py_iden_consensus(todolist):
+    """iden_consensus AS:1139-1158 -> lines 'y,z,iden' (distance() with mode='HW', AS:224-234)."""
+    def dist_hw(X1, X2):
+        A1, A2 = (X2, X1) if len(X1) > len(X2) else (X1, X2)
+        return round(1 - py_hw(A1, A2) / len(A2), 3)
+
+    lines = []
+    for A1, A2, y, z in todolist:
+        idenlist = [dist_hw(A1, A2), dist_hw(A1, py_compl_reverse(A2))]
+        idenlist.sort(reverse=True)
+        if idenlist[0] >= 0.60:
+            lines.append(str(y) + "," + str(z) + "," + str(idenlist[0]))
+    return lines

@@ -58,6 +58,15 @@ def main():
 
         if "process_consensuslist" in os.environ.get("ASB200_STAGES", "process_list,process_consensuslist"):
             ns["process_consensuslist"] = process_consensuslist
+        if "iden_consensus" in os.environ.get("ASB200_STAGES", "iden_consensus"):
+            original_do_parallel = ns["do_parallel"]
+
+            def do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename):
+                if getattr(worker, "__name__", "") != "iden_consensus":
+                    return original_do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename)
+                return host.iden_consensus_files(outputfolder, consensus_tempfile, stringx, engine=OracleEngine())
+
+            ns["do_parallel"] = do_parallel
 
     inner_pl = ns["process_list"]
     inner_sg = ns["sort_groups"]

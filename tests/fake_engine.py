@@ -79,5 +79,17 @@ class OracleEngine:
         recs = np.array(rows, dtype=RECORD) if rows else np.empty(0, dtype=RECORD)
         return recs, {"pairs": int(q.shape[0]), "n_records": len(rows)}
 
+    def distance_pairs(self, a, b, strand=None, mode="NW"):
+        out = np.empty(len(a), dtype=np.int32)
+        for p in range(len(a)):
+            x = self.buf[self.offs[a[p]]:self.offs[a[p] + 1]].tobytes()
+            y = self.buf[self.offs[b[p]]:self.offs[b[p] + 1]].tobytes()
+            if len(x) > len(y):
+                x, y = y, x
+            if strand is not None and strand[p]:
+                y = oracle.compl_reverse(y)
+            out[p] = oracle.hw(x, y) if mode == "HW" else oracle.nw(x, y, "myers")
+        return out
+
     def close(self):
         self.closed = True

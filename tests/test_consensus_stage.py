@@ -82,3 +82,68 @@ def test_threeway_pairs_any_length_order(engine):
         want, _ = fe.threeway_pairs(q, t, dpass, drev)
         util.assert_same_records(got, want)
         assert info["pairs"] == q.shape[0] and len(want) > 10
+
+
+def make_todolist(seed, n=40, L=150):
+    """[A1, A2, y, z] entries as comp_consensus_groups / compare_consensus spool them (AS:1275-1299)."""
+    rng = np.random.default_rng(seed)
+    base = [rng.integers(0, 4, int(L * f), dtype=np.uint8) for f in (1.0, 1.1, 0.8, 1.0, 1.25)]
+    cons = []
+    for i in range(n):
+        r = synth.mutate(rng, base[i % len(base)], sub=0.03, ins=0.01, dele=0.01)
+        if i % 3 == 0:
+            r = r[10:-5]  # nested consensus: HW must find it inside the longer one
+        if rng.random() < 0.5:
+            r = synth.revcomp_codes(r)
+        cons.append(ACGT[r].tobytes().decode())
+    cons[3] = cons[3][:20] + "N" + cons[3][21:]
+    return [[cons[y], cons[z], y, z] for y in range(n) for z in range(y + 1, n) if (y + z) % 3 != 1]
+
+
+def run_iden(engine, todolist, tmp_path):
+    import pickle
+    with open(os.path.join(str(tmp_path), "file_0.todo"), "wb") as f:
+        pickle.dump(todolist, f)
+    host.iden_consensus_files(str(tmp_path), "consensus.tmp", "...comparing consensuses ", engine=engine)
+    assert not os.path.exists(os.path.join(str(tmp_path), "file_0.todo"))
+    return open(os.path.join(str(tmp_path), "consensus.tmp")).read().splitlines()
+
+
+def test_hw_oracle_definition():
+    assert oracle.py_hw("ACGT", "TTACGTTT") == 0 and oracle.hw(b"ACGT", b"TTACGTTT") == 0
+    assert oracle.py_hw("ACGT", "TTAGGTTT") == 1 and oracle.hw(b"ACGT", b"TTAGGTTT") == 1
+    rng = np.random.default_rng(5)
+    for _ in range(40):
+        q = ACGT[rng.integers(0, 4, int(rng.integers(1, 40)))].tobytes()
+        t = ACGT[rng.integers(0, 4, int(rng.integers(40, 90)))].tobytes()
+        assert oracle.hw(q, t) == oracle.py_hw(q.decode(), t.decode())
+
+
+def test_host_iden_consensus_matches_restatement(tmp_path):
+    todo = make_todolist(1, n=16, L=60)
+    assert run_iden(OracleEngine(), todo, tmp_path) == oracle.py_iden_consensus(todo)
+
+
+@pytest.mark.gpu
+def test_product_iden_consensus_matches_restatement(engine, tmp_path):
+    todo = make_todolist(2, n=30, L=150)
+    want = oracle.py_iden_consensus(todo)
+    assert run_iden(engine, todo, tmp_path) == want and len(want) > 20
+
+
+@pytest.mark.gpu
+def test_hw_distance_pairs(engine):
+    rng = np.random.default_rng(9)
+    reads = util.random_reads(rng, 40, 30, 700, families=3, err=0.05) + [b"ACGT", b"TTACGTTT", b"A" * 33, b"C"]
+    reads += [reads[0][40:300], reads[1][5:-7]]
+    buf, offs = synth.pack_reads(reads)
+    engine.upload_reads(buf, offs)
+    n = len(reads)
+    a = rng.integers(0, n, 500).astype(np.uint32)
+    b = rng.integers(0, n, 500).astype(np.uint32)
+    strand = rng.integers(0, 2, 500).astype(np.uint8)
+    got = engine.distance_pairs(a, b, strand, mode="HW")
+    fe = OracleEngine()
+    fe.upload_reads(buf, offs)
+    want = fe.distance_pairs(a, b, strand, mode="HW")
+    assert np.array_equal(got, want)
