@@ -882,7 +882,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
             const int W = (int)((ctx->h_len[r1] + 31) / 32);
             const int c2 = class_for(std::min(need_words(ctx, r1, ctx->h_pmax_dpass, 0), W));
             if (c2 != cls) break;
-            if (r1 > r0 && pairs + cnt > ctx->pair_cap) break;
+            if (r1 > r0 && pairs + cnt > ctx->pair_cap * ctx->world) break;  // pair_cap is per rank
             zneed = std::max(zneed, std::min(need_words(ctx, r1, ctx->h_pmax_drev, 1), W));
             wmax = std::max<uint32_t>(wmax, (uint32_t)W);
         }
@@ -893,7 +893,8 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
         ++r1;
     }
     const int zcls = class_for(zneed);
-    const uint64_t cap = std::max<uint64_t>(pairs, 32);
+    // this rank owns every world-th group: at most ceil(groups/world) groups of 32 pairs
+    const uint64_t cap = std::max<uint64_t>(std::min<uint64_t>(pairs, ((groups + ctx->world - 1) / ctx->world) * 32), 32);
     int rc = ensure_lists(ctx, cap);
     if (rc) return rc;
     CU(ctx->d_grp.ensure(prefix.size()));
