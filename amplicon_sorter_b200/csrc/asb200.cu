@@ -639,7 +639,9 @@ int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint3
     return ASB_OK;
 }
 
-int odd_stride(int w) { return w | 1; }
+// Peq row stride: rows of the (<= 4 common) symbols land 8 banks apart, so lanes whose windows sit on
+// different symbols AND a few words apart still hit distinct banks
+int odd_stride(int w) { int v = (w & ~31) + 8; return v >= w ? v : v + 32; }
 
 }  // namespace
 

@@ -132,7 +132,8 @@ __device__ __forceinline__ void cols32_dispatch(const int len, uint32_t (&Pv)[NB
 // work accumulates columns x active words executed per lane (warp-uniform) for the work counters.
 //
 // Active range.  The registers Pv[0..len) / Mv[0..len) hold the words base .. base+len-1; nothing
-// else is computed.  For a cell let LB(r, c) = D'[r][c] + |r - r*(c)|, r*(c) = m - (n - c): no path
+// else is computed.  `len` is warp-uniform (one code path), `base` is per lane: each lane keeps its
+// registers on its OWN live rows, so the 32 lanes only have to agree on how many words they need.  For a cell let LB(r, c) = D'[r][c] + |r - r*(c)|, r*(c) = m - (n - c): no path
 // through a cell with LB > k ends with cost <= k.  D' is non-decreasing along diagonals and
 // |r - r*| is constant along them, so LB is non-decreasing along diagonals; the cells of word t in
 // columns (c, c+32] lie on diagonals that cross column c inside words t-1 and t.  Hence, with
@@ -152,8 +153,11 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
     const int Bmax = BT > 0 ? BT : g.Bw;
     uint32_t Pv[NB], Mv[NB];
     const int wm = (m - 1) >> 5;  // word holding row m
-    int base = 0;                 // absolute index of word Pv[0]
-    int len = min(min(Bmax, g.T0 + 1), wm + 1);
+    // this lane's own Ukkonen band: rows c - Dl .. c + El
+    const int el = on ? (k - abs(n - m)) >> 1 : 0;
+    const int Dl = el + max(n - m, 0), El = el + max(m - n, 0);
+    int base = 0;  // absolute index of word Pv[0] -- PER LANE: every lane keeps its registers on its own live rows
+    int len = min(min(Bmax, g.T0 + 1), wm + 1);  // words computed per column -- warp-uniform (shared code path)
     if (BT > 0) len = min(BT, BT - ((BT - len) / STEP) * STEP);
 #pragma unroll
     for (int t = 0; t < Bmax; ++t) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; }
@@ -206,9 +210,10 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
             }
         }
         work += 32ull * (unsigned)len;
-        // ---- which words can still carry a path of cost <= k ?
-        int fa = 0x7FFFFFFF, la = -1;
+        // ---- which of this lane's words can still carry a path of cost <= k ?
+        int ntop = base, need = 0;
         if (alive) {
+            int fa = 0x7FFFFFFF, la = -1;
             const int rstar = m - (n - c);
             int bst = topoff + c;  // score on the boundary above word t
 #pragma unroll
@@ -225,39 +230,41 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
                     bst = bsb;
                 }
             }
-            alive = la >= 0;
+            if (la >= 0) {
+                // next block: [first alive, last alive + 1], clipped to the rows its columns c+1..c+32 can use
+                ntop = max(base + fa, (c - Dl) > 0 ? (c - Dl) >> 5 : 0);
+                const int nbot = min(base + la + 1, min(wm, (c + 31 + El) >> 5));
+                // row 0 (D[0][c] = c) is a boundary, not a word: diagonals leaving it inside the next block
+                // enter word 0, and its cells can be live up to column Dl -- keep word 0 until then
+                if (c < Dl + 1) ntop = 0;
+                need = nbot - ntop + 1;
+            }
+            alive = need > 0;  // nothing live inside the band: this lane is > k
+            if (!alive) { ntop = base; need = 0; }
         }
         const unsigned am = __ballot_sync(0xFFFFFFFFu, alive);
         if (am == 0u) break;
         if (__popc(am) <= push_thresh) break;
-        // ---- active range of the next block (absolute word indices), clipped to Ukkonen's band
-        int ntop = base + __reduce_min_sync(0xFFFFFFFFu, fa);
-        int nbot = base + __reduce_max_sync(0xFFFFFFFFu, la) + 1;
-        // rows needed by columns c+1 .. c+32: [c+1-Dmax, c+32+Emax]
-        const int gtop = (c - g.Dmax) > 0 ? (c - g.Dmax) >> 5 : 0;
-        const int gbot = min(wm, (c + 31 + g.Emax) >> 5);
-        ntop = max(ntop, gtop);
-        nbot = min(nbot, gbot);
-        // row 0 (D[0][c] = c) is a boundary, not a word: diagonals leaving it inside the next block enter
-        // word 0, and its cells can be live up to column Dmax -- keep word 0 until then
-        if (c < g.Dmax + 1) ntop = 0;
-        if (nbot < ntop) break;  // nothing live inside the band: every undecided lane is > k
-        int nlen = nbot - ntop + 1;
+        int nlen = __reduce_max_sync(0xFFFFFFFFu, need);
         if (BT > 0) nlen = min(BT, BT - ((BT - nlen) / STEP) * STEP);  // round up to a compiled variant
         nlen = min(nlen, Bmax);
-        // drop dead words at the top: the boundary moves down by their vertical deltas, registers shift
-        for (int d = ntop - base; d > 0; --d) {
-            topoff += __popc(Pv[0]) - __popc(Mv[0]);
+        // drop this lane's dead words at the top: its boundary moves down by their vertical deltas
+        const int drop = ntop - base;
+        const int maxdrop = __reduce_max_sync(0xFFFFFFFFu, drop);
+        int valid = len;  // words of this lane that hold computed state
+        for (int d = 0; d < maxdrop; ++d) {
+            if (d < drop) {
+                topoff += __popc(Pv[0]) - __popc(Mv[0]);
 #pragma unroll
-            for (int t = 0; t + 1 < Bmax; ++t) { Pv[t] = Pv[t + 1]; Mv[t] = Mv[t + 1]; }
-            --len;
+                for (int t = 0; t + 1 < Bmax; ++t) { Pv[t] = Pv[t + 1]; Mv[t] = Mv[t + 1]; }
+                --valid;
+            }
         }
-        if (len < 0) { topoff += 32 * (-len); len = 0; }  // whole range replaced: boundary rows are +1 apart
         base = ntop;
-        // grow the bottom: words entering start from vertical +1 edges (shrinking needs no bookkeeping)
+        // words entering at the bottom start from vertical +1 edges (shrinking needs no bookkeeping)
 #pragma unroll
         for (int t = 0; t < Bmax; ++t) {
-            if (t >= len && t < nlen) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; }
+            if (t >= valid && t < nlen) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; }
         }
         len = nlen;
     }
