@@ -90,6 +90,7 @@ __device__ __forceinline__ void build_peq(uint32_t* peq, const DevBatch& B, cons
 {
     const int lane = threadIdx.x & 31;
     const int words = (B.sigma + 1) * B.Wpad;
+    __syncwarp();  // every lane is done reading the previous query's table (racecheck: WAR hazard otherwise)
     for (int x = lane; x < words; x += 32) peq[x] = 0u;
     __syncwarp();
     for (int w = lane; w < W; w += 32) {
