@@ -58,6 +58,7 @@ struct DevBatch {
     uint32_t n_tasks, rank, world;
     int screen_cols_num;  // screen runs at most ceil(nmax * num / 256) columns
     int push_thresh;
+    int cont_thresh;
     // list task space
     const uint64_t* list; const uint32_t* list_val; uint64_t list_n;
     const uint8_t* ex_strand; int32_t* ex_out;  // M_EXACT
@@ -179,10 +180,12 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         return;
     }
     g.ncols = full_cols;
+    g.tcut = 0x7FFFFFFF;
+    g.cont = 0;
     int push = 0;
     if (mode == M_SCREEN) {
-        const int lim = (((nmax * B.screen_cols_num) >> 8) + 31) & ~31;
-        g.ncols = min(full_cols, max(lim, 32));
+        g.tcut = max(32, (((nmax * B.screen_cols_num) >> 8) + 31) & ~31);
+        g.cont = B.cont_thresh;
         push = B.push_thresh;
     }
     build_peq(peq, B, q, m, W);
@@ -505,8 +508,9 @@ struct asb_ctx {
     int sm_count = 148;
     // params
     uint64_t pair_cap = 1ull << 26;
-    double screen_frac = 0.62;
+    double screen_frac = 0.5;
     int push_thresh = 1;
+    int cont_thresh = 4;  // measured: cfg2/3/4 = 41.6 / 156 / 151 M pairs/s (14: 36 / 129 / 153; always continue: 38 / 163 / 126)
     // reads
     uint32_t n_reads = 0, sigma = 0, max_len = 0;
     uint8_t code_to_ascii[257];
@@ -694,6 +698,7 @@ int asb_set_param(asb_ctx* ctx, const char* name, double value)
     if (!strcmp(name, "pair_cap")) { if (value < 1024) return fail(ctx, ASB_E_ARG, "pair_cap too small"); ctx->pair_cap = (uint64_t)value; }
     else if (!strcmp(name, "screen_frac")) { if (value <= 0 || value > 1) return fail(ctx, ASB_E_ARG, "screen_frac in (0,1]"); ctx->screen_frac = value; }
     else if (!strcmp(name, "push_thresh")) { if (value < 0 || value > 31) return fail(ctx, ASB_E_ARG, "push_thresh in [0,31]"); ctx->push_thresh = (int)value; }
+    else if (!strcmp(name, "cont_thresh")) { if (value < 0 || value > 32) return fail(ctx, ASB_E_ARG, "cont_thresh in [0,32]"); ctx->cont_thresh = (int)value; }
     else return fail(ctx, ASB_E_ARG, "unknown parameter %s", name);
     return ASB_OK;
 }
@@ -915,6 +920,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     B.n_tasks = groups > ctx->rank ? (uint32_t)((groups - ctx->rank + ctx->world - 1) / ctx->world) : 0;
     B.screen_cols_num = std::max(1, (int)(ctx->screen_frac * 256.0 + 0.5));
     B.push_thresh = ctx->push_thresh;
+    B.cont_thresh = ctx->cont_thresh;
     const int bt = kClasses[cls];
     B.Wpad = odd_stride((int)wmax + (bt > 0 ? bt : 0) + 1);
 

@@ -28,6 +28,8 @@ struct BandGeom {
     int Bw;     // window words available (== BT when BT > 0)
     int ncols;  // warp-uniform number of columns to run (multiple of 32)
     int T0;     // last word the first 32 columns can touch
+    int tcut;   // screening checkpoint column: from here on the pass only continues while ...
+    int cont;   // ... more than `cont` lanes are undecided (packing them into list warps is cheaper otherwise)
 };
 
 // One Myers word-update.  hin arrives as the top bits of the previous word's Ph/Mh (php/mhp) so
@@ -127,7 +129,9 @@ __device__ __forceinline__ void cols32_dispatch(const int len, uint32_t (&Pv)[NB
 //   n, k   : this lane's target length (n >= m) and threshold; on = lane participates
 //   g      : warp-uniform band geometry (every participating lane's band fits in it)
 //   push_thresh : screening -- stop at a 32-column boundary once at most push_thresh lanes are
-//            undecided (they are reported as PASS_SURVIVOR)
+//            undecided (they are reported as PASS_SURVIVOR); from column g.tcut on, also when at most
+//            g.cont lanes are undecided: finishing a pass for a few related lanes wastes the other
+//            lanes, while >= ~14 undecided lanes are cheaper to finish in place than to redo in lists
 // Returns status (per lane) and, for PASS_DONE, the score D'[m][n].
 // work accumulates columns x active words executed per lane (warp-uniform) for the work counters.
 //
@@ -245,6 +249,7 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
         const unsigned am = __ballot_sync(0xFFFFFFFFu, alive);
         if (am == 0u) break;
         if (__popc(am) <= push_thresh) break;
+        if (c >= g.tcut && __popc(am) <= g.cont) break;
         int nlen = __reduce_max_sync(0xFFFFFFFFu, need);
         if (BT > 0) nlen = min(BT, BT - ((BT - nlen) / STEP) * STEP);  // round up to a compiled variant
         nlen = min(nlen, Bmax);

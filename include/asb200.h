@@ -60,7 +60,7 @@ typedef struct {
 int asb_create(int device, void *stream, asb_ctx **out);
 void asb_destroy(asb_ctx *ctx);
 const char *asb_last_error(const asb_ctx *ctx);
-/* Tuning knobs: "pair_cap", "screen_frac", "push_thresh", "count_words". */
+/* Tuning knobs (results never depend on them): "pair_cap", "screen_frac", "push_thresh", "cont_thresh". */
 int asb_set_param(asb_ctx *ctx, const char *name, double value);
 
 /* Replaces the per-record `str(record.seq).upper()` payload (:551) + per-pair compl_reverse (:795):

@@ -15,7 +15,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--cfg", type=int, default=5)
 ap.add_argument("--scale", type=float, default=0.2)
 ap.add_argument("--frac", type=float, nargs="*", default=[0.62])
-ap.add_argument("--push", type=int, nargs="*", default=[3])
+ap.add_argument("--push", type=int, nargs="*", default=[1])
+ap.add_argument("--cont", type=int, nargs="*", default=[4])
 ap.add_argument("--check", action="store_true")
 a = ap.parse_args()
 t0 = time.time()
@@ -27,14 +28,16 @@ t0 = time.time()
 eng.upload_reads(buf, offs)
 print(f"upload {time.time()-t0:.3f}s")
 for frac in a.frac:
+  for cont in a.cont:
     for push in a.push:
         eng.set_param("screen_frac", frac)
         eng.set_param("push_thresh", push)
+        eng.set_param("cont_thresh", cont)
         for rep in range(2):
             t0 = time.time()
             recs, tot = eng.compare_batch(order, hi, dpass, drev)
             dt = time.time() - t0
-        tot.update(frac=frac, push=push, wall_s=round(dt, 4), pairs_per_s=round(tot["pairs"] / dt / 1e6, 2),
+        tot.update(frac=frac, push=push, cont=cont, wall_s=round(dt, 4), pairs_per_s=round(tot["pairs"] / dt / 1e6, 2),
                    wu_per_s_T=round(tot["word_updates"] / (tot["total_ms"] / 1e3) / 1e12, 3))
         print(json.dumps(tot), flush=True)
 if a.check:

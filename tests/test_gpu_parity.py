@@ -96,11 +96,9 @@ def test_screen_parameters_do_not_change_results(engine):
     """Early-termination / survivor routing is an optimisation: any setting gives identical records."""
     reads, _, _ = synth.make_config(1, scale=0.25)
     want, _ = util.oracle_batch(reads)
-    for frac, push in ((0.2, 0), (0.4, 31), (1.0, 0), (0.62, 3), (0.05, 8)):
-        got, _ = util.gpu_batch(engine, reads, screen_frac=frac, push_thresh=push)
+    for frac, push, cont in ((0.2, 0, 0), (0.4, 31, 32), (1.0, 0, 14), (0.62, 3, 32), (0.05, 8, 1), (0.5, 1, 14)):
+        got, _ = util.gpu_batch(engine, reads, screen_frac=frac, push_thresh=push, cont_thresh=cont)
         util.assert_same_records(got, want)
-    engine.set_param("screen_frac", 0.62)
-    engine.set_param("push_thresh", 1)
 
 
 def test_small_pair_cap_multi_step_and_sharding(engine):
