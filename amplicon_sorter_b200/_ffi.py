@@ -17,7 +17,7 @@ class StepInfo(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("n_records", C.c_uint64), ("fwd_survivors", C.c_uint64),
                 ("rc_survivors", C.c_uint64), ("zone_checks", C.c_uint64), ("word_updates", C.c_uint64),
                 ("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("screen_ms", C.c_float), ("total_ms", C.c_float),
-                ("launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("launches", C.c_uint32), ("reserved", C.c_uint32), ("screen_word_updates", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -940,6 +940,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     rc = read_counters(ctx);
     if (rc) return rc;
+    info->screen_word_updates = ctx->h_ctr[C_WORDS] * 32ull;
     rc = finish_lists(ctx, B, cls, zcls, (int)wmax, ctx->h_ctr[C_F], info);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -100,7 +100,7 @@ class Engine:
         self.batch_begin(order, hi, dpass, drev, rank, world)
         recs = []
         tot = {"pairs": 0, "n_records": 0, "fwd_survivors": 0, "rc_survivors": 0, "zone_checks": 0,
-               "word_updates": 0, "screen_ms": 0.0, "total_ms": 0.0, "steps": 0}
+               "word_updates": 0, "screen_word_updates": 0, "screen_ms": 0.0, "total_ms": 0.0, "steps": 0}
         while True:
             info = self.batch_step()
             if info is None:

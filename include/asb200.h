@@ -53,6 +53,7 @@ typedef struct {
     float total_ms;          /* device time of the whole step */
     uint32_t launches;       /* this library's own kernels launched by the step (cub sorts not counted) */
     uint32_t reserved;
+    uint64_t screen_word_updates; /* the part of word_updates executed by asb_screen alone */
 } asb_step_info;
 
 /* Replaces nothing in the reference (it has no device): create/destroy an engine on `device`.
