@@ -614,16 +614,23 @@ int read_counters(asb_ctx* ctx)
     return ASB_OK;
 }
 
-size_t smem_bytes(const asb_ctx* ctx, int Wpad) { return (size_t)kWarpsPerBlock * (ctx->sigma + 1) * Wpad * sizeof(uint32_t); }
+struct LaunchShape { int warps; size_t smem; int grid; };
 
-template <typename F> int launch_cfg(asb_ctx* ctx, F fn, size_t smem, int* grid)
+// Every warp owns a Peq table of (sigma+1) x Wpad words.  8 warps per block normally; large alphabets or
+// very long reads fall back to fewer warps per block so that the tables still fit in shared memory.
+template <typename F> int launch_cfg(asb_ctx* ctx, F fn, int Wpad, LaunchShape* shape)
 {
-    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * 32, smem));
-    if (per_sm < 1) return fail(ctx, ASB_E_TOO_LONG, "kernel does not fit on an SM (shared memory %zu bytes)", smem);
-    *grid = per_sm * ctx->sm_count;
-    return ASB_OK;
+    for (int warps = kWarpsPerBlock; warps >= 1; warps >>= 1) {
+        const size_t smem = (size_t)warps * (ctx->sigma + 1) * Wpad * sizeof(uint32_t);
+        if (smem > 227 * 1024) continue;
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
+        if (per_sm < 1) continue;
+        shape->warps = warps; shape->smem = smem; shape->grid = per_sm * ctx->sm_count;
+        return ASB_OK;
+    }
+    return fail(ctx, ASB_E_TOO_LONG, "match-mask table of one query (%u symbols x %d words) does not fit in shared memory", ctx->sigma + 1, Wpad);
 }
 
 int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint32_t* vals, uint64_t n)
@@ -632,13 +639,12 @@ int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint3
     B.list = keys; B.list_val = vals; B.list_n = n;
     CU(cudaMemsetAsync(ctx->d_ctr.p + C_TASK, 0, sizeof(unsigned long long), ctx->stream));
     lists_fn fn = Fns::lists(cls);
-    const size_t smem = smem_bytes(ctx, B.Wpad);
-    int grid = 0;
-    int rc = launch_cfg(ctx, fn, smem, &grid);
+    LaunchShape ls;
+    int rc = launch_cfg(ctx, fn, B.Wpad, &ls);
     if (rc) return rc;
-    const uint64_t slices = (n + 31) / 32, blocks = (slices + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    grid = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint64_t>(blocks, 1));
-    fn<<<grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(B, mode);
+    const uint64_t slices = (n + 31) / 32, blocks = (slices + ls.warps - 1) / ls.warps;
+    const int grid = (int)std::min<uint64_t>((uint64_t)ls.grid, std::max<uint64_t>(blocks, 1));
+    fn<<<grid, ls.warps * 32, ls.smem, ctx->stream>>>(B, mode);
     CU(cudaGetLastError());
     ctx->launches++;
     return ASB_OK;
@@ -927,13 +933,12 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (B.n_tasks) {
         screen_fn fn = Fns::screen(cls);
-        const size_t smem = smem_bytes(ctx, B.Wpad);
-        int grid = 0;
-        rc = launch_cfg(ctx, fn, smem, &grid);
+        LaunchShape ls;
+        rc = launch_cfg(ctx, fn, B.Wpad, &ls);
         if (rc) return rc;
-        const uint64_t blocks = ((uint64_t)B.n_tasks + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        grid = (int)std::min<uint64_t>((uint64_t)grid, std::max<uint64_t>(blocks, 1));
-        fn<<<grid, kWarpsPerBlock * 32, smem, ctx->stream>>>(B);
+        const uint64_t blocks = ((uint64_t)B.n_tasks + ls.warps - 1) / ls.warps;
+        const int grid = (int)std::min<uint64_t>((uint64_t)ls.grid, std::max<uint64_t>(blocks, 1));
+        fn<<<grid, ls.warps * 32, ls.smem, ctx->stream>>>(B);
         CU(cudaGetLastError());
         ctx->launches++;
     }

@@ -211,3 +211,32 @@ def test_kmer_side_output_matches_its_oracle(engine, k):
     # same template, opposite strands share almost everything; unrelated reads share little (k=8)
     if k == 8:
         assert engine.kmer_shared_pairs([0], [n - 1])[0] == oracle.kmer_shared(reads[0], reads[0], k)
+
+
+def test_degenerate_batches(engine):
+    """Empty, singleton and no-partner batches: no step runs, no records (AS:673 loops over range(0,-1))."""
+    from amplicon_sorter_b200 import thresholds as th
+    dpass, drev = th.tables(0.8, 500)
+    buf, offs = synth.pack_reads([b"ACGT" * 80, b"ACGT" * 100])  # 320 vs 400: outside the 5 % window
+    engine.upload_reads(buf, offs)
+    for order, hi in (([], []), ([0], [0]), ([0, 1], [0, 1])):
+        recs, tot = engine.compare_batch(np.array(order, np.uint32), np.array(hi, np.uint32), dpass, drev)
+        assert len(recs) == 0 and tot["pairs"] == 0 and tot["steps"] == 0
+
+
+def test_large_alphabet_uses_fewer_warps_per_block(engine):
+    """edlib semantics: every distinct byte is its own symbol.  60 symbols x long reads still fit (fewer warps/block)."""
+    rng = np.random.default_rng(91)
+    al = np.frombuffer(bytes(range(48, 108)), dtype=np.uint8)
+    base = [al[rng.integers(0, al.size, 900)] for _ in range(3)]
+    reads = []
+    for i in range(60):
+        r = base[i % 3].copy()
+        pos = rng.integers(0, 900, 40)
+        r[pos] = al[rng.integers(0, al.size, 40)]
+        reads.append(r.tobytes())
+    got, tot = util.gpu_batch(engine, reads)
+    want, st = util.oracle_batch(reads)
+    assert tot["pairs"] == st["pairs"]
+    util.assert_same_records(got, want)
+    assert len(want) > 300
