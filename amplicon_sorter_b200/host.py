@@ -45,7 +45,8 @@ def _iden_table(lens_sorted: np.ndarray, records: np.ndarray, dcap: np.ndarray |
     if dcap is not None and dcap.shape[0] > lmax:
         # emitted distances never exceed the pass cut-off of their length: no scan of d needed
         present = np.bincount(L, minlength=lmax + 1) > 0
-        dmax = np.where(present, dcap[: lmax + 1].astype(np.int64), -1)
+        cap = dcap[: lmax + 1].astype(np.int64)
+        dmax = np.where(present & (cap < 0x7FFFFFFF), cap, -1)  # 0xFFFFFFFF = no distance passes for that length
     else:
         dmax = np.zeros(lmax + 1, dtype=np.int64) - 1
         np.maximum.at(dmax, L, d)
