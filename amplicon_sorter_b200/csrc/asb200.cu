@@ -654,6 +654,11 @@ int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint3
 // different symbols AND a few words apart still hit distinct banks
 int odd_stride(int w) { int v = (w & ~31) + 8; return v >= w ? v : v + 32; }
 
+// Words per Peq row for queries of up to `wmax` words run with window class `bt`: every lane keeps its own
+// window position, so a lane sitting on the last query word still reads `window - 1` (zero) words past it.
+// bt == 0 (window in local memory) can be as wide as the query itself.
+int peq_stride(int wmax, int bt) { return odd_stride(wmax + (bt > 0 ? bt : wmax) + 1); }
+
 }  // namespace
 
 extern "C" {
@@ -858,7 +863,7 @@ static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, 
     {
         const int zbt = kClasses[zcls];
         DevBatch BZ = B;
-        BZ.Wpad = odd_stride(wmax + (zbt > 0 ? zbt : 0) + 1);
+        BZ.Wpad = peq_stride(wmax, zbt);
         rc = run_list(ctx, BZ, M_ZONE, zcls, keys, vals, nZ); if (rc) return rc;
     }
     rc = read_counters(ctx); if (rc) return rc;
@@ -928,7 +933,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     B.push_thresh = ctx->push_thresh;
     B.cont_thresh = ctx->cont_thresh;
     const int bt = kClasses[cls];
-    B.Wpad = odd_stride((int)wmax + (bt > 0 ? bt : 0) + 1);
+    B.Wpad = peq_stride((int)wmax, bt);
 
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (B.n_tasks) {
@@ -1183,7 +1188,7 @@ int asb_threeway_pairs(asb_ctx* ctx, const uint32_t* q, const uint32_t* t, uint6
     B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
     B.ctr = ctx->d_ctr.p; B.list_cap = ctx->list_cap;
     const int bt = kClasses[cls];
-    B.Wpad = odd_stride((int)wmax + (bt > 0 ? bt : 0) + 1);
+    B.Wpad = peq_stride((int)wmax, bt);
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = finish_lists(ctx, B, cls, zcls, (int)wmax, npairs, info);
     if (rc) return rc;
@@ -1230,7 +1235,7 @@ int asb_distance_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const
     memset(&B, 0, sizeof B);
     B.codes_f = ctx->d_cf.p; B.codes_r = ctx->d_cr.p; B.pos_off = ctx->d_pos_off.p; B.pos_len = ctx->d_pos_len.p;
     B.n = n; B.sigma = ctx->sigma; B.ctr = ctx->d_ctr.p; B.ex_strand = d_st.p; B.ex_out = d_out.p; B.ex_hw = mode;
-    B.Wpad = odd_stride((int)wmax + 1);
+    B.Wpad = peq_stride((int)wmax, 0);
     int rc = run_list(ctx, B, M_EXACT, kNumClasses - 1, d_keys.p, nullptr, npairs);
     if (rc) return rc;
     rc = read_counters(ctx);
