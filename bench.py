@@ -256,6 +256,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- resident-input arm -------------------------------------------------------------------
+    codes_bytes = 2 * int(w["buf"].nbytes)  # forward + compl_reverse symbol codes
+    flush_buf = None if codes_bytes > 126 * (1 << 20) else torch.empty(192 * (1 << 20), dtype=torch.uint8, device=dev)
     eng.upload_reads(h_buf, h_offs)
     for _ in range(a.warmup):
         job()
@@ -267,6 +269,8 @@ def main():
     t0 = time.perf_counter()
     ev0.record(stream)
     for _ in range(a.steps):
+        if flush_buf is not None:
+            flush_buf.zero_()  # inputs smaller than L2 (reduced --reads only): evict them between timed steps
         out = job(agg)
     ev1.record(stream)
     barrier()
@@ -330,7 +334,8 @@ def main():
                 "dtype": "u32", "data": "synthetic",
                 "config": {"workload": f"cfg5: --all on {w['n_reads']} synthetic ~1 kb reads (200 templates, 6% ONT-like error, both strands, 1% with N), -sg 80; one step = the whole {w['tl']}-pair job",
                            "reads": w["n_reads"], "pairs_per_step": w["tl"], "records_per_step": n_records, "mean_read_len": w["mean_len"],
-                           "l2_policy": "inputs (2 x %.0f MB symbol codes) exceed L2; no flush needed" % (w["buf"].nbytes / 1e6),
+                           "l2_policy": ("inputs (2 x %.0f MB symbol codes) exceed the 126 MB L2; no flush needed" % (w["buf"].nbytes / 1e6)) if flush_buf is None
+                           else "inputs fit in L2: a 192 MB buffer is overwritten between timed steps",
                            "sharding": "32-target groups of every row dealt cyclically over ranks; NCCL gather of records to rank 0"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline}
         if not a.no_cpu:
