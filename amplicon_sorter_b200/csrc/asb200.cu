@@ -533,7 +533,6 @@ struct asb_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // last step's sorted records on device
     uint64_t* rec_keys = nullptr; uint32_t* rec_vals = nullptr; uint64_t rec_n = 0;
-    asb_record* h_stage = nullptr; size_t h_stage_n = 0;  // pinned staging
     uint32_t launches = 0;  // own kernels launched since the last step began
     DevBuf<uint32_t> d_kbits; int kmer_k = 0; uint32_t kmer_words = 0;  // K2 bitsets
     DevBuf<uint64_t> d_roff_all; DevBuf<uint32_t> d_rlen_all;
@@ -697,7 +696,6 @@ void asb_destroy(asb_ctx* ctx)
     ctx->d_O.release(); ctx->d_alt.release(); ctx->d_Zv.release(); ctx->d_Ov.release(); ctx->d_altv.release(); ctx->d_ctr.release();
     ctx->d_tmp.release(); ctx->d_rec.release(); ctx->d_kbits.release(); ctx->d_roff_all.release(); ctx->d_rlen_all.release();
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -3,15 +3,17 @@
 // Replaces edlib.align(query, target, task='distance', mode='NW') as called by distance()
 // (/root/reference/amplicon_sorter.py:224-234, call at :231).  One LANE owns one (query, target)
 // pair; the 32 lanes of a warp share the QUERY (its match masks Peq live in shared memory, one
-// conflict-free LDS per word-update) and differ in the target.  The DP column is held as a
-// sliding window of 32-row words in registers (BT > 0) or local memory (BT == 0, any width).
+// conflict-free LDS per word-update) and differ in the target.  Each lane holds only the ACTIVE
+// words of its DP column in registers (BT > 0: at most BT words) or local memory (BT == 0).
 //
-// Exactness: the window realises Ukkonen's band for threshold k (rows c-(n-m)-e .. c+e of column
-// c, e = (k-(n-m))/2).  Cells outside the window are treated as reachable only through +1 edges
-// (virtual hin = +1 at the top, Pv = all-ones for a word entering at the bottom), i.e. we solve a
-// shortest-path problem on a sub-graph of the edit graph: every computed value is an upper bound
-// of the true D[r][c] and equals it whenever the true value is <= k.  So "score <= k" is decided
-// exactly and the score is the exact distance whenever it is <= k.
+// Exactness (full argument in DESIGN.md section 2): for threshold k call a cell viable if
+// D[r][c] + |r - r*(c)| <= k, r*(c) = m - (n - c).  Viable cells are closed under "optimal
+// predecessor", every computed value is a shortest path in a sub-graph of the edit graph (cells
+// outside the registers are only reachable through +1 edges: hin = +1 above the first word,
+// Pv = all-ones for an entering word) and therefore an upper bound that is exact on viable cells as
+// long as all viable cells are computed -- which the active-range rule in band_pass guarantees.
+// The final cell is viable iff d <= k: "d <= k" is decided exactly and the score is the exact
+// distance whenever it is <= k.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>

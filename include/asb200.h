@@ -8,7 +8,8 @@
  * ctypes stub.  Plain pointers and sizes only; no C++/torch types; no
  * exceptions cross the boundary -- every entry point returns an asb_status.
  *
- * Threading: a context owns one CUDA device + stream and is NOT re-entrant.
+ * Threading: a context owns one CUDA device + stream and is NOT re-entrant.  asb_upload_reads,
+ * asb_threeway_pairs and asb_distance_pairs end a batch that asb_batch_begin started.
  * There is no CPU fallback anywhere behind this header.
  */
 #ifndef ASB200_H
