@@ -63,6 +63,14 @@ struct DevBatch {
     const uint64_t* list; const uint32_t* list_val; uint64_t list_n;
     const uint8_t* ex_strand; int32_t* ex_out;  // M_EXACT
     int ex_hw;                                  // M_EXACT: 1 = edlib HW (infix) distance
+    // seed lower bound (K2 put to work, see myers_band.cuh::SeedLB): per-read q-mer presence bitsets and the
+    // seed codes of both strands, 8 per uint4 chunk, chunks of read r from seed_off[r]
+    const uint32_t* qbits; const uint4* seeds_f; const uint4* seeds_r; const uint32_t* seed_off;
+    const uint32_t* pos_read;  // [n] read id at sorted position p (nullptr: positions are read ids)
+    int seed_on;               // 0 = off
+    int seed_J;                // chunk entries per lane in shared memory
+    // shared memory per warp: [peq_words match masks][kSeedBitsPad query bitset][seed_J * 16 words of profiles]
+    int peq_words, warp_words;
 };
 
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
@@ -189,13 +197,38 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         push = B.push_thresh;
     }
     build_peq(peq, B, q, m, W);
+    // seed lower bound: the query's q-mer presence bitset goes next to its match masks
+    SeedLB sl;
+    sl.hs = nullptr; sl.J = 0;
+    const bool use_seeds = B.seed_on && mode != M_EXACT && mode != M_ZONE;
+    uint32_t* qb = peq + B.peq_words;
+    uint16_t* hs_lane = reinterpret_cast<uint16_t*>(qb + kSeedBitsPad) + (threadIdx.x & 31);
+    const uint4* sf = nullptr;
+    const uint4* sr = nullptr;
+    int nch = 0;
+    if (use_seeds) {
+        const uint32_t rid = B.pos_read ? B.pos_read[row] : row;
+        const uint4* src = reinterpret_cast<const uint4*>(B.qbits + (size_t)rid * kSeedWords);
+        for (int x = threadIdx.x & 31; x < kSeedBitsPad / 4; x += 32)
+            reinterpret_cast<uint4*>(qb)[x] = x < kSeedWords / 4 ? __ldg(src + x) : make_uint4(~0u, ~0u, ~0u, ~0u);
+        __syncwarp();
+        if (job.valid) {
+            const uint32_t tid = B.pos_read ? B.pos_read[job.j] : job.j;
+            const uint32_t so = B.seed_off[tid];
+            sf = B.seeds_f + so;
+            sr = B.seeds_r + so;
+            nch = (n / kSeedQ + 7) >> 3;
+        }
+        sl.hs = hs_lane;
+    }
 
     // One call site for both strands (keeps a single copy of the unrolled pass in the instruction cache).
 #pragma unroll 1
     for (int phase = (mode == M_RC ? 1 : 0); phase < 2; ++phase) {
         const uint8_t* t = (phase == 1 || (mode == M_EXACT && job.strand)) ? tr : tf;
         int st, sc;
-        band_pass<BT>(peq, B.Wpad, W, m, t, n, k, ok, g, push, st, sc, cols_acc);
+        if (use_seeds) sl.J = seed_profile(qb, (t == tr) ? sr : sf, ok ? nch : 0, hs_lane, B.seed_J);
+        band_pass<BT>(peq, B.Wpad, W, m, t, n, k, ok, g, push, sl, st, sc, cols_acc);
         const bool pass = ok && st == PASS_DONE && sc <= k;
         const bool surv = ok && st == PASS_SURVIVOR;
         if (phase == 0) {
@@ -224,12 +257,13 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
 // --------------------------------------------------------------------------------------------
 // asb_screen: persistent warps pull (row, 32 consecutive targets) tasks from an atomic counter.
 // --------------------------------------------------------------------------------------------
+// BT <= 9 (the 1 kb classes): 64 registers = 4 blocks of 8 warps per SM
 template <int BT>
-__global__ void __launch_bounds__(256) asb_screen(const DevBatch B)
+__global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? 4 : 1) asb_screen(const DevBatch B)
 {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t* peq = smem + wid * ((B.sigma + 1) * B.Wpad);
+    uint32_t* peq = smem + wid * B.warp_words;
     unsigned long long cols_acc = 0;
     for (;;) {
         unsigned long long t = 0;
@@ -263,7 +297,7 @@ __global__ void __launch_bounds__(256) asb_lists(const DevBatch B, const int mod
 {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t* peq = smem + wid * ((B.sigma + 1) * B.Wpad);
+    uint32_t* peq = smem + wid * B.warp_words;
     unsigned long long cols_acc = 0;
     const unsigned long long n_slices = (B.list_n + 31) >> 5;
     for (;;) {
@@ -364,6 +398,56 @@ __global__ void __launch_bounds__(256) asb_kmer_build_kernel(const uint8_t* __re
         }
         __syncthreads();
         for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) bits[(uint64_t)r * words + w] = sm[w];
+        __syncthreads();
+    }
+}
+
+// Seed tables for the admissible lower bound (myers_band.cuh::SeedLB).  Per read: the presence bitset of
+// all its forward-strand q-mers (a row's query is always the forward strand) and, for both strands, the
+// q-mer code of every disjoint seed s (bases s*q .. s*q+q-1), 8 codes per uint4 chunk; seeds holding a
+// non-ACGT symbol and the padding of the last chunk get kSeedInvalid ("always present").  One block per read.
+__global__ void __launch_bounds__(256) asb_seed_build_kernel(const uint8_t* __restrict__ cf, const uint8_t* __restrict__ cr,
+                                                           const uint64_t* __restrict__ roff, const uint32_t* __restrict__ rlen,
+                                                           const uint32_t* __restrict__ seed_off, uint32_t n_reads,
+                                                           const uint8_t* __restrict__ base2, uint32_t* __restrict__ qbits,
+                                                           uint16_t* __restrict__ seeds_f, uint16_t* __restrict__ seeds_r)
+{
+    __shared__ uint32_t sm[kSeedWords];
+    for (uint32_t r = blockIdx.x; r < n_reads; r += gridDim.x) {
+        for (int w = threadIdx.x; w < kSeedWords; w += blockDim.x) sm[w] = 0u;
+        __syncthreads();
+        const uint8_t* f = cf + roff[r];
+        const uint8_t* v = cr + roff[r];
+        const int len = (int)rlen[r];
+        for (int p = threadIdx.x; p + kSeedQ <= len; p += blockDim.x) {
+            uint32_t code = 0;
+            bool ok = true;
+#pragma unroll
+            for (int t = 0; t < kSeedQ; ++t) {
+                const uint32_t b = base2[f[p + t]];
+                ok = ok && b < 4u;
+                code = (code << 2) | (b & 3u);
+            }
+            if (ok) atomicOr(&sm[code >> 5], 1u << (code & 31));
+        }
+        const int S = len / kSeedQ, slots = ((S + 7) >> 3) << 3;
+        for (int sd = threadIdx.x; sd < slots; sd += blockDim.x) {
+            uint32_t code = 0, cv = 0;
+            bool ok = sd < S, okv = sd < S;
+            if (sd < S) {
+#pragma unroll
+                for (int t = 0; t < kSeedQ; ++t) {
+                    const uint32_t b = base2[f[sd * kSeedQ + t]], bv = base2[v[sd * kSeedQ + t]];
+                    ok = ok && b < 4u; okv = okv && bv < 4u;
+                    code = (code << 2) | (b & 3u); cv = (cv << 2) | (bv & 3u);
+                }
+            }
+            const size_t o = (size_t)seed_off[r] * 8 + sd;
+            seeds_f[o] = (uint16_t)(ok ? code : kSeedInvalid);
+            seeds_r[o] = (uint16_t)(okv ? cv : kSeedInvalid);
+        }
+        __syncthreads();
+        for (int w = threadIdx.x; w < kSeedWords; w += blockDim.x) qbits[(size_t)r * kSeedWords + w] = sm[w];
         __syncthreads();
     }
 }
@@ -535,6 +619,8 @@ struct asb_ctx {
     uint64_t* rec_keys = nullptr; uint32_t* rec_vals = nullptr; uint64_t rec_n = 0;
     uint32_t launches = 0;  // own kernels launched since the last step began
     DevBuf<uint32_t> d_kbits; int kmer_k = 0; uint32_t kmer_words = 0;  // K2 bitsets
+    DevBuf<uint32_t> d_qbits, d_seed_off, d_order; DevBuf<uint16_t> d_seeds_f, d_seeds_r; DevBuf<uint8_t> d_base2;  // seed lower bound
+    bool seeds_ready = false; int seed_lb = 1;
     DevBuf<uint64_t> d_roff_all; DevBuf<uint32_t> d_rlen_all;
     DevBuf<asb_record> d_rec;
 };
@@ -617,10 +703,10 @@ struct LaunchShape { int warps; size_t smem; int grid; };
 
 // Every warp owns a Peq table of (sigma+1) x Wpad words.  8 warps per block normally; large alphabets or
 // very long reads fall back to fewer warps per block so that the tables still fit in shared memory.
-template <typename F> int launch_cfg(asb_ctx* ctx, F fn, int Wpad, LaunchShape* shape)
+template <typename F> int launch_cfg(asb_ctx* ctx, F fn, const DevBatch& B, LaunchShape* shape)
 {
     for (int warps = kWarpsPerBlock; warps >= 1; warps >>= 1) {
-        const size_t smem = (size_t)warps * (ctx->sigma + 1) * Wpad * sizeof(uint32_t);
+        const size_t smem = (size_t)warps * B.warp_words * sizeof(uint32_t);
         if (smem > 227 * 1024) continue;
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
@@ -629,7 +715,7 @@ template <typename F> int launch_cfg(asb_ctx* ctx, F fn, int Wpad, LaunchShape* 
         shape->warps = warps; shape->smem = smem; shape->grid = per_sm * ctx->sm_count;
         return ASB_OK;
     }
-    return fail(ctx, ASB_E_TOO_LONG, "match-mask table of one query (%u symbols x %d words) does not fit in shared memory", ctx->sigma + 1, Wpad);
+    return fail(ctx, ASB_E_TOO_LONG, "match-mask table of one query (%u symbols x %d words) does not fit in shared memory", ctx->sigma + 1, B.Wpad);
 }
 
 int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint32_t* vals, uint64_t n)
@@ -639,7 +725,7 @@ int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint3
     CU(cudaMemsetAsync(ctx->d_ctr.p + C_TASK, 0, sizeof(unsigned long long), ctx->stream));
     lists_fn fn = Fns::lists(cls);
     LaunchShape ls;
-    int rc = launch_cfg(ctx, fn, B.Wpad, &ls);
+    int rc = launch_cfg(ctx, fn, B, &ls);
     if (rc) return rc;
     const uint64_t slices = (n + 31) / 32, blocks = (slices + ls.warps - 1) / ls.warps;
     const int grid = (int)std::min<uint64_t>((uint64_t)ls.grid, std::max<uint64_t>(blocks, 1));
@@ -657,6 +743,60 @@ int odd_stride(int w) { int v = (w & ~31) + 8; return v >= w ? v : v + 32; }
 // window position, so a lane sitting on the last query word still reads `window - 1` (zero) words past it.
 // bt == 0 (window in local memory) can be as wide as the query itself.
 int peq_stride(int wmax, int bt) { return odd_stride(wmax + (bt > 0 ? bt : wmax) + 1); }
+
+// Shared-memory layout of one warp (DevBatch::peq_words / warp_words) for Peq stride `Wpad`; `seeds` adds the
+// query's q-mer bitset and the per-lane seed profiles (only when the seed tables of the uploaded reads exist).
+void set_layout(const asb_ctx* ctx, DevBatch& B, int Wpad, bool seeds)
+{
+    B.Wpad = Wpad;
+    B.peq_words = (int)(((ctx->sigma + 1) * (uint32_t)Wpad + 3u) & ~3u);
+    B.seed_on = seeds && ctx->seed_lb && ctx->seeds_ready;
+    B.seed_J = std::min<int>(kSeedMaxChunks, std::max<int>(1, (int)((ctx->max_len / kSeedQ + 7) >> 3)));
+    B.warp_words = B.peq_words + (B.seed_on ? kSeedBitsPad + B.seed_J * 16 : 0);
+    B.qbits = ctx->d_qbits.p; B.seed_off = ctx->d_seed_off.p;
+    B.seeds_f = reinterpret_cast<const uint4*>(ctx->d_seeds_f.p); B.seeds_r = reinterpret_cast<const uint4*>(ctx->d_seeds_r.p);
+}
+
+// 2-bit base of a symbol code (A,C,G,T = 0..3; anything else, and the padding code sigma, = 4)
+void fill_base2(const asb_ctx* ctx, uint8_t* base2)
+{
+    memset(base2, 4, 256);
+    for (uint32_t c = 0; c < ctx->sigma && c < 256; ++c) {
+        const uint8_t ch = ctx->code_to_ascii[c];
+        base2[c] = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
+    }
+}
+
+// Builds the seed tables of the uploaded reads once per upload (first step that wants them).
+int ensure_seeds(asb_ctx* ctx)
+{
+    if (!ctx->seed_lb || ctx->seeds_ready || ctx->n_reads == 0) return ASB_OK;
+    const uint32_t n = ctx->n_reads;
+    std::vector<uint32_t> off((size_t)n + 1, 0);
+    for (uint32_t r = 0; r < n; ++r) {
+        const uint64_t next = (uint64_t)off[r] + ((ctx->h_rlen[r] / kSeedQ + 7) >> 3);
+        if (next > 0xFFFFFFF0ull) return fail(ctx, ASB_E_TOO_LONG, "seed tables exceed 32-bit chunk offsets");
+        off[r + 1] = (uint32_t)next;
+    }
+    const size_t chunks = (size_t)off[n] + 1;  // + one chunk of slack
+    CU(ctx->d_qbits.ensure((size_t)n * kSeedWords)); CU(ctx->d_seed_off.ensure((size_t)n + 1));
+    CU(ctx->d_seeds_f.ensure(chunks * 8)); CU(ctx->d_seeds_r.ensure(chunks * 8)); CU(ctx->d_base2.ensure(256));
+    CU(ctx->d_roff_all.ensure((size_t)n + 1)); CU(ctx->d_rlen_all.ensure(n));
+    uint8_t base2[256];
+    fill_base2(ctx, base2);
+    CU(cudaMemcpyAsync(ctx->d_base2.p, base2, 256, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_seed_off.p, off.data(), sizeof(uint32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_roff_all.p, ctx->h_roff.data(), sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_rlen_all.p, ctx->h_rlen.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    asb_seed_build_kernel<<<std::min<uint32_t>(n, (uint32_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+        ctx->d_cf.p, ctx->d_cr.p, ctx->d_roff_all.p, ctx->d_rlen_all.p, ctx->d_seed_off.p, n, ctx->d_base2.p, ctx->d_qbits.p,
+        ctx->d_seeds_f.p, ctx->d_seeds_r.p);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));  // `off` and `base2` are locals
+    ctx->launches++;
+    ctx->seeds_ready = true;
+    return ASB_OK;
+}
 
 }  // namespace
 
@@ -695,6 +835,7 @@ void asb_destroy(asb_ctx* ctx)
     ctx->d_dpass.release(); ctx->d_drev.release(); ctx->d_grp.release(); ctx->d_F.release(); ctx->d_R.release(); ctx->d_Z.release();
     ctx->d_O.release(); ctx->d_alt.release(); ctx->d_Zv.release(); ctx->d_Ov.release(); ctx->d_altv.release(); ctx->d_ctr.release();
     ctx->d_tmp.release(); ctx->d_rec.release(); ctx->d_kbits.release(); ctx->d_roff_all.release(); ctx->d_rlen_all.release();
+    ctx->d_qbits.release(); ctx->d_seed_off.release(); ctx->d_order.release(); ctx->d_seeds_f.release(); ctx->d_seeds_r.release(); ctx->d_base2.release();
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -707,6 +848,7 @@ int asb_set_param(asb_ctx* ctx, const char* name, double value)
     if (!strcmp(name, "pair_cap")) { if (value < 1024) return fail(ctx, ASB_E_ARG, "pair_cap too small"); ctx->pair_cap = (uint64_t)value; }
     else if (!strcmp(name, "screen_frac")) { if (value <= 0 || value > 1) return fail(ctx, ASB_E_ARG, "screen_frac in (0,1]"); ctx->screen_frac = value; }
     else if (!strcmp(name, "push_thresh")) { if (value < 0 || value > 31) return fail(ctx, ASB_E_ARG, "push_thresh in [0,31]"); ctx->push_thresh = (int)value; }
+    else if (!strcmp(name, "seed_lb")) { ctx->seed_lb = value != 0; }
     else if (!strcmp(name, "cont_thresh")) { if (value < 0 || value > 32) return fail(ctx, ASB_E_ARG, "cont_thresh in [0,32]"); ctx->cont_thresh = (int)value; }
     else return fail(ctx, ASB_E_ARG, "unknown parameter %s", name);
     return ASB_OK;
@@ -731,6 +873,7 @@ int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, u
     }
     ctx->max_len = max_len;
     ctx->kmer_k = 0;
+    ctx->seeds_ready = false;
     const uint64_t total = ctx->h_roff[n_reads] + (((uint64_t)max_len + 31) & ~31ull) + 128;  // over-read slack for short lanes
     DevBuf<uint8_t> d_ascii; DevBuf<uint64_t> d_offs, d_roff; DevBuf<uint32_t> d_present; DevBuf<uint8_t> d_maps;
     struct Guard { DevBuf<uint8_t>&a; DevBuf<uint64_t>&b,&c; DevBuf<uint32_t>&d; DevBuf<uint8_t>&e; ~Guard(){a.release();b.release();c.release();d.release();e.release();} } guard{d_ascii, d_offs, d_roff, d_present, d_maps};
@@ -810,9 +953,10 @@ int asb_batch_begin(asb_ctx* ctx, const uint32_t* order, uint32_t n, const uint3
         b = std::max(b, drev[L]);
         ctx->h_pmax_dpass[L] = a; ctx->h_pmax_drev[L] = b;
     }
-    CU(ctx->d_pos_off.ensure(n)); CU(ctx->d_pos_len.ensure(n)); CU(ctx->d_hi.ensure(n));
+    CU(ctx->d_pos_off.ensure(n)); CU(ctx->d_pos_len.ensure(n)); CU(ctx->d_hi.ensure(n)); CU(ctx->d_order.ensure(n));
     CU(ctx->d_dpass.ensure(table_len)); CU(ctx->d_drev.ensure(table_len));
     if (n) {
+        CU(cudaMemcpyAsync(ctx->d_order.p, order, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_pos_off.p, pos_off.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_pos_len.p, ctx->h_len.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_hi.p, hi, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -861,7 +1005,7 @@ static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, 
     {
         const int zbt = kClasses[zcls];
         DevBatch BZ = B;
-        BZ.Wpad = peq_stride(wmax, zbt);
+        set_layout(ctx, BZ, peq_stride(wmax, zbt), false);
         rc = run_list(ctx, BZ, M_ZONE, zcls, keys, vals, nZ); if (rc) return rc;
     }
     rc = read_counters(ctx); if (rc) return rc;
@@ -910,9 +1054,11 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
         ++r1;
     }
     const int zcls = class_for(zneed);
+    int rc = ensure_seeds(ctx);
+    if (rc) return rc;
     // this rank owns every world-th group: at most ceil(groups/world) groups of 32 pairs
     const uint64_t cap = std::max<uint64_t>(std::min<uint64_t>(pairs, ((groups + ctx->world - 1) / ctx->world) * 32), 32);
-    int rc = ensure_lists(ctx, cap);
+    rc = ensure_lists(ctx, cap);
     if (rc) return rc;
     CU(ctx->d_grp.ensure(prefix.size()));
     CU(cudaMemcpyAsync(ctx->d_grp.p, prefix.data(), sizeof(uint32_t) * prefix.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -931,13 +1077,14 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     B.push_thresh = ctx->push_thresh;
     B.cont_thresh = ctx->cont_thresh;
     const int bt = kClasses[cls];
-    B.Wpad = peq_stride((int)wmax, bt);
+    set_layout(ctx, B, peq_stride((int)wmax, bt), true);
+    B.pos_read = ctx->d_order.p;
 
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (B.n_tasks) {
         screen_fn fn = Fns::screen(cls);
         LaunchShape ls;
-        rc = launch_cfg(ctx, fn, B.Wpad, &ls);
+        rc = launch_cfg(ctx, fn, B, &ls);
         if (rc) return rc;
         const uint64_t blocks = ((uint64_t)B.n_tasks + ls.warps - 1) / ls.warps;
         const int grid = (int)std::min<uint64_t>((uint64_t)ls.grid, std::max<uint64_t>(blocks, 1));
@@ -1076,10 +1223,7 @@ int asb_kmer_build(asb_ctx* ctx, int k)
     CU(ctx->d_kbits.ensure((size_t)std::max<uint32_t>(n, 1) * words));
     CU(ctx->d_roff_all.ensure((size_t)n + 1)); CU(ctx->d_rlen_all.ensure(std::max<uint32_t>(n, 1)));
     uint8_t base2[256];
-    for (uint32_t c = 0; c <= ctx->sigma && c < 256; ++c) {
-        const uint8_t ch = ctx->code_to_ascii[c];
-        base2[c] = (c == ctx->sigma) ? 4 : (ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4);
-    }
+    fill_base2(ctx, base2);
     DevBuf<uint8_t> d_b2;
     struct Guard { DevBuf<uint8_t>& a; ~Guard() { a.release(); } } guard{d_b2};
     CU(d_b2.ensure(256));
@@ -1169,7 +1313,9 @@ int asb_threeway_pairs(asb_ctx* ctx, const uint32_t* q, const uint32_t* t, uint6
         }
     }
     const int cls = class_for(need), zcls = class_for(zneed);
-    int rc = ensure_lists(ctx, std::max<uint64_t>(npairs, 32));
+    int rc = ensure_seeds(ctx);
+    if (rc) return rc;
+    rc = ensure_lists(ctx, std::max<uint64_t>(npairs, 32));
     if (rc) return rc;
     CU(ctx->d_pos_off.ensure(n)); CU(ctx->d_pos_len.ensure(n));
     CU(ctx->d_dpass.ensure(table_len)); CU(ctx->d_drev.ensure(table_len));
@@ -1186,7 +1332,7 @@ int asb_threeway_pairs(asb_ctx* ctx, const uint32_t* q, const uint32_t* t, uint6
     B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
     B.ctr = ctx->d_ctr.p; B.list_cap = ctx->list_cap;
     const int bt = kClasses[cls];
-    B.Wpad = peq_stride((int)wmax, bt);
+    set_layout(ctx, B, peq_stride((int)wmax, bt), true);  // positions are read ids: pos_read stays null
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = finish_lists(ctx, B, cls, zcls, (int)wmax, npairs, info);
     if (rc) return rc;
@@ -1233,7 +1379,7 @@ int asb_distance_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const
     memset(&B, 0, sizeof B);
     B.codes_f = ctx->d_cf.p; B.codes_r = ctx->d_cr.p; B.pos_off = ctx->d_pos_off.p; B.pos_len = ctx->d_pos_len.p;
     B.n = n; B.sigma = ctx->sigma; B.ctr = ctx->d_ctr.p; B.ex_strand = d_st.p; B.ex_out = d_out.p; B.ex_hw = mode;
-    B.Wpad = peq_stride((int)wmax, 0);
+    set_layout(ctx, B, peq_stride((int)wmax, 0), false);
     int rc = run_list(ctx, B, M_EXACT, kNumClasses - 1, d_keys.p, nullptr, npairs);
     if (rc) return rc;
     rc = read_counters(ctx);

@@ -24,6 +24,57 @@ constexpr int kMaxDynWords = 512;  // BT == 0: window words kept in local memory
 
 enum PassStatus : int { PASS_DEAD = 0, PASS_DONE = 1, PASS_SURVIVOR = 2 };
 
+// Seed lower bound -- the k-mer stage used the only way it can be used exactly: as an
+// ADMISSIBLE bound, never as a decision.  The target is cut into disjoint q-mers ("seeds", seed s =
+// columns s*q+1 .. s*q+q).  A seed that occurs nowhere in the query cannot be aligned without an edit,
+// and edits inside different seeds are different edits, so from ANY cell of column c the remaining cost
+// is at least H(c) = number of such seeds lying wholly to the right of column c (s >= ceil(c/q)).
+// H only ever ends a lane early ("every computed cell of this column has D' + max(|r - r*|, H) > k"):
+// if d <= k, the cell where an optimal path leaves column c is computed exactly (the active-range
+// rule does not use H) and satisfies D + remaining = d <= k, so the test cannot fire.  Unrelated 1 kb
+// reads leave ~94 % of their 7-mers unmatched: H(0) ~ 134 of k = 200, and a lane is proven > k after
+// ~180 columns instead of ~400.
+//
+// Per lane and strand, seed_profile() turns the target's seed codes (HBM, 8 per uint4 "chunk") and the
+// query's q-mer presence bitset (shared memory) into one u16 per chunk j in shared memory:
+//   bits 8..15 = absent mask of the chunk's 8 seeds, bits 0..7 = min(255, absent seeds in chunks > j).
+constexpr int kSeedQ = 7;                                // seed length
+constexpr int kSeedWords = (1 << (2 * kSeedQ)) / 32;     // 4^q-bit presence bitset per read (2 KB)
+constexpr int kSeedBitsPad = kSeedWords + 4;             // + one all-ones word (index kSeedWords) for invalid seeds, 16-byte padded
+constexpr uint32_t kSeedInvalid = 1u << (2 * kSeedQ);    // seed code of "holds a non-ACGT symbol / runs past the read": always present
+constexpr int kSeedMaxChunks = 64;                       // seeds beyond column 8*q*64 = 3584 are ignored (still admissible)
+
+struct SeedLB {
+    const uint16_t* hs;  // shared memory, this lane's column: entry of chunk j at hs[32 * j]
+    int J;               // warp-uniform number of chunks stored; 0 = bound not in use
+};
+
+// Must be called by all 32 lanes.  seeds: this lane's target strand (nullptr / nch == 0: lane idle).
+__device__ __forceinline__ int seed_profile(const uint32_t* __restrict__ qbits, const uint4* __restrict__ seeds, const int nch,
+                                            uint16_t* __restrict__ hs_lane, const int maxJ)
+{
+    const int J = min(__reduce_max_sync(0xFFFFFFFFu, nch), maxJ);
+    int cnt = 0;
+    for (int j = J - 1; j >= 0; --j) {
+        uint32_t mask = 0u;
+        if (j < nch) {
+            const uint4 v = __ldg(seeds + j);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            uint32_t present = 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t lo = w[i] & 0xFFFFu, hi = w[i] >> 16;
+                present |= (__funnelshift_r(qbits[lo >> 5], 0u, lo) & 1u) << (2 * i);
+                present |= (__funnelshift_r(qbits[hi >> 5], 0u, hi) & 1u) << (2 * i + 1);
+            }
+            mask = present ^ 0xFFu;
+        }
+        hs_lane[32 * j] = (uint16_t)((mask << 8) | (uint32_t)min(cnt, 255));
+        cnt += __popc(mask);
+    }
+    return J;
+}
+
 struct BandGeom {
     int Dmax;   // max over lanes of (n-m)+e : band reaches rows >= c - Dmax
     int Emax;   // max over lanes of e       : band reaches rows <= c + Emax
@@ -134,24 +185,32 @@ __device__ __forceinline__ void cols32_dispatch(const int len, uint32_t (&Pv)[NB
 //            undecided (they are reported as PASS_SURVIVOR); from column g.tcut on, also when at most
 //            g.cont lanes are undecided: finishing a pass for a few related lanes wastes the other
 //            lanes, while >= ~14 undecided lanes are cheaper to finish in place than to redo in lists
+//   sl     : seed lower bound of this lane's target strand (sl.J == 0: not in use), see SeedLB
 // Returns status (per lane) and, for PASS_DONE, the score D'[m][n].
 // work accumulates columns x active words executed per lane (warp-uniform) for the work counters.
 //
 // Active range.  The registers Pv[0..len) / Mv[0..len) hold the words base .. base+len-1; nothing
 // else is computed.  `len` is warp-uniform (one code path), `base` is per lane: each lane keeps its
-// registers on its OWN live rows, so the 32 lanes only have to agree on how many words they need.  For a cell let LB(r, c) = D'[r][c] + |r - r*(c)|, r*(c) = m - (n - c): no path
-// through a cell with LB > k ends with cost <= k.  D' is non-decreasing along diagonals and
-// |r - r*| is constant along them, so LB is non-decreasing along diagonals; the cells of word t in
-// columns (c, c+32] lie on diagonals that cross column c inside words t-1 and t.  Hence, with
-// "alive" = the word may hold a cell with LB <= k for some undecided lane (word-level test:
-// min D' >= (A + B - 32)/2 for boundary scores A, B), the next 32 columns need exactly the words
-// [first alive, last alive + 1], intersected with Ukkonen's band for those columns.  Words dropped
-// at the top never come back; a word (re-)entering at the bottom starts from Pv = all-ones (vertical
-// +1 edges below the word above): an upper bound that is exact wherever a cost <= k path can run.
+// registers on its OWN live rows, so the 32 lanes only have to agree on how many words they need.
+// Every computed value D' is a shortest path in a sub-graph of the edit graph, i.e. an upper bound of D.
+// Let P be an optimal path of cost d <= k, X_c its last cell in column c.  Every cell Y of P satisfies
+// D(Y) + max(|r - r*|, H) <= d <= k   (r*(c) = m - (n - c); H = seed bound of Y's column, see SeedLB).
+// Word tests at a 32-column boundary c (min D' over a word >= (A + B - 32)/2 for its boundary scores A, B):
+//   strong: dlow + max(gd, H(c)) <= k      weak: dlow + gd <= k      (gd = min |r - r*| over the word)
+// Range of the next 32 columns = [first strongly alive, last weakly alive + 1], inside Ukkonen's band:
+//   * top: P never moves up, and X_c (exact by induction along P) passes the strong test, so nothing above
+//     the first strongly alive word is ever needed again;
+//   * bottom: a cell Y of P in a later column back-projects along its diagonal onto Q in column c.  If Q
+//     lies above X_c, Y is at most one word below X_c's word.  Otherwise the computed column contains the
+//     vertical run X_c -> Q, so D'(Q) <= D(X_c) + (rows between) <= D(Y), and |r - r*| is the same on a
+//     diagonal: Q's word passes the weak test, and Y is at most one word below it.  (H must NOT be used at
+//     the bottom: it shrinks with c, so a bound that holds for Y's column need not hold at column c.)
+// Words dropped at the top never come back; a word (re-)entering at the bottom starts from Pv = all-ones
+// (vertical +1 edges below the word above).  With H = 0 this is the rule proven in DESIGN.md section 2.
 template <int BT>
 __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, const int Wpad, const int W, const int m,
                                        const uint8_t* __restrict__ tgt, const int n, const int k, const bool on,
-                                       const BandGeom g, const int push_thresh, int& status, int& score,
+                                       const BandGeom g, const int push_thresh, const SeedLB sl, int& status, int& score,
                                        unsigned long long& work)
 {
     constexpr int NB = BT > 0 ? BT : kMaxDynWords;
@@ -220,6 +279,11 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
         int ntop = base, need = 0;
         if (alive) {
             int fa = 0x7FFFFFFF, la = -1;
+            int H = 0;  // absent seeds wholly right of column c
+            {
+                const int s0 = (c + kSeedQ - 1) / kSeedQ, j = s0 >> 3;
+                if (j < sl.J) { const uint32_t v = sl.hs[32 * j]; H = (int)(v & 255u) + __popc((v >> 8) >> (s0 & 7)); }
+            }
             const int rstar = m - (n - c);
             int bst = topoff + c;  // score on the boundary above word t
 #pragma unroll
@@ -231,18 +295,21 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
                     const int gd2 = rstar - hi;
                     gd = gd > gd2 ? gd : gd2;
                     gd = gd > 0 ? gd : 0;
-                    const int lb = ((bst + bsb - 32 + 1) >> 1) + gd;
-                    if (lb <= k) { la = t; fa = fa > t ? t : fa; }
+                    const int dlow = (bst + bsb - 32 + 1) >> 1;  // lower bound of D' over the word
+                    if (dlow + gd <= k) la = t;                                    // weak test: bottom of the range
+                    if (dlow + (gd > H ? gd : H) <= k) fa = fa > t ? t : fa;       // strong test: top of the range
                     bst = bsb;
                 }
             }
+            // no word passes the strong test: every computed cell has D' + max(|r - r*|, H) > k, this lane is > k
+            if (fa == 0x7FFFFFFF) la = -1;
             if (la >= 0) {
-                // next block: [first alive, last alive + 1], clipped to the rows its columns c+1..c+32 can use
+                // next block: [first strongly alive, last weakly alive + 1], clipped to the rows its columns c+1..c+32 can use
                 ntop = max(base + fa, (c - Dl) > 0 ? (c - Dl) >> 5 : 0);
                 const int nbot = min(base + la + 1, min(wm, (c + 31 + El) >> 5));
-                // row 0 (D[0][c] = c) is a boundary, not a word: diagonals leaving it inside the next block
-                // enter word 0, and its cells can be live up to column Dl -- keep word 0 until then
-                if (c < Dl + 1) ntop = 0;
+                // row 0 (D[0][c] = c) is a boundary, not a word: a path leaving it inside the next block enters
+                // word 0 -- keep word 0 while the row-0 cell itself can be on a path of cost <= k
+                if (c < Dl + 1 && c + H <= k) ntop = 0;
                 need = nbot - ntop + 1;
             }
             alive = need > 0;  // nothing live inside the band: this lane is > k

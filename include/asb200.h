@@ -62,7 +62,8 @@ typedef struct {
 int asb_create(int device, void *stream, asb_ctx **out);
 void asb_destroy(asb_ctx *ctx);
 const char *asb_last_error(const asb_ctx *ctx);
-/* Tuning knobs (results never depend on them): "pair_cap", "screen_frac", "push_thresh", "cont_thresh". */
+/* Tuning knobs (results never depend on them): "pair_cap", "screen_frac", "push_thresh", "cont_thresh",
+ * "seed_lb" (1/0: use the admissible q-mer seed lower bound to end hopeless alignments early). */
 int asb_set_param(asb_ctx *ctx, const char *name, double value);
 
 /* Replaces the per-record `str(record.seq).upper()` payload (:551) + per-pair compl_reverse (:795):

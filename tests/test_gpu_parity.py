@@ -240,3 +240,57 @@ def test_large_alphabet_uses_fewer_warps_per_block(engine):
     assert tot["pairs"] == st["pairs"]
     util.assert_same_records(got, want)
     assert len(want) > 300
+
+
+def test_seed_bound_is_only_an_optimisation(engine):
+    """The q-mer seed lower bound (myers_band.cuh::SeedLB) may only end hopeless alignments earlier:
+    identical records with and without it, and fewer word-updates with it."""
+    try:
+        for cfg, scale, sg in ((5, 0.012, 80.0), (1, 0.25, 80.0), (4, 0.012, 96.0), (3, 0.03, 90.0)):
+            reads, _, _ = synth.make_config(cfg, scale=scale)
+            want, _ = util.oracle_batch(reads, sg)
+            off, t0 = util.gpu_batch(engine, reads, sg, seed_lb=0)
+            on, t1 = util.gpu_batch(engine, reads, sg, seed_lb=1)
+            util.assert_same_records(off, want)
+            util.assert_same_records(on, want)
+            assert t1["word_updates"] <= t0["word_updates"]
+            if cfg == 5:
+                assert t1["word_updates"] < 0.8 * t0["word_updates"], (t0["word_updates"], t1["word_updates"])
+    finally:
+        engine.set_param("seed_lb", 1)
+
+
+def test_seed_bound_adversarial_edges(engine):
+    """Pairs built so that the bound is TIGHT: every edit destroys a different seed of the target and the
+    distance sits exactly on / one above the cut-off.  d == dpass must still be emitted (admissibility)."""
+    rng = np.random.default_rng(77)
+    al = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = {65: 84, 84: 65, 67: 71, 71: 67}
+    q_len = 7
+    for L, sg in ((994, 96.0), (700, 90.0), (1001, 80.0), (350, 97.0)):
+        dp, _ = thresholds.tables(sg / 100, L + 64)
+        k = int(dp[L])
+        q = al[rng.integers(0, 4, L)]
+        reads = [q.tobytes()]
+        n_seeds = L // q_len
+        for extra in (-1, 0, 1, 2):
+            for kind in ("sub", "mixed"):
+                t = q.copy()
+                want_d = k + extra - (2 if kind == "mixed" else 0)  # the grid shift below costs 2 edits
+                seeds = rng.permutation(n_seeds)
+                # one substitution inside each of `want_d` different seeds (wraps around if k > #seeds)
+                for e in range(want_d):
+                    s = int(seeds[e % n_seeds])
+                    p = s * q_len + (e // n_seeds * 3 + int(rng.integers(0, 2))) % q_len
+                    t[p] = al[(int(np.where(al == t[p])[0][0]) + 1 + int(rng.integers(0, 3))) % 4]
+                tb = t.tobytes()
+                if kind == "mixed":  # shift the seed grid: delete the first base, append one
+                    tb = tb[1:] + b"A"
+                reads.append(tb)
+                reads.append(oracle.compl_reverse(tb))             # same pair through the ':reverse' branch
+                reads.append(tb[: L // 2] + b"N" + tb[L // 2 + 1:])  # a seed with a non-ACGT symbol
+        reads += util.random_reads(rng, 20, L - 10, L + 10)
+        want, _ = util.oracle_batch(reads, sg)
+        got, _ = util.gpu_batch(engine, reads, sg, seed_lb=1)
+        util.assert_same_records(got, want)
+        assert len(want) > 8 and k - 1 in want["d"].tolist() and k in want["d"].tolist()
