@@ -205,6 +205,11 @@ __device__ __forceinline__ void cols32_dispatch(const int len, uint32_t (&Pv)[NB
 //     vertical run X_c -> Q, so D'(Q) <= D(X_c) + (rows between) <= D(Y), and |r - r*| is the same on a
 //     diagonal: Q's word passes the weak test, and Y is at most one word below it.  (H must NOT be used at
 //     the bottom: it shrinks with c, so a bound that holds for Y's column need not hold at column c.)
+//     Induction over the boundaries keeps every such Q inside the computed column: Q's own back-projection one
+//     boundary earlier was computed and weakly alive (or above that boundary's X), so Q's word was in the range,
+//     and Ukkonen's clip never removes it (D(Q) + |r - r*| <= k).  A seed-based clip WOULD (Q is not on P):
+//     measured, a seed band at the bottom + the then necessary "take the band when the last computed word is
+//     alive" rule gained 1 % with seeds and lost 7 % without -- not used.
 // Words dropped at the top never come back; a word (re-)entering at the bottom starts from Pv = all-ones
 // (vertical +1 edges below the word above).  With H = 0 this is the rule proven in DESIGN.md section 2.
 template <int BT>
@@ -222,6 +227,17 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
     const int el = on ? (k - abs(n - m)) >> 1 : 0;
     const int Dl = el + max(n - m, 0), El = el + max(m - n, 0);
     int base = 0;  // absolute index of word Pv[0] -- PER LANE: every lane keeps its registers on its own live rows
+    bool alive = on;
+    const auto seeds_right_of = [&](const int col) -> int {
+        const int s0 = (col + kSeedQ - 1) / kSeedQ, j = s0 >> 3;
+        if (j >= sl.J) return 0;
+        const uint32_t v = sl.hs[32 * j];
+        return (int)(v & 255u) + __popc((v >> 8) >> (s0 & 7));
+    };
+    if (sl.J > 0) {
+        if (seeds_right_of(0) > k) alive = false;  // more absent seeds than edits allowed: d > k without any DP
+        if (__ballot_sync(0xFFFFFFFFu, alive) == 0u) { status = PASS_DEAD; score = 0; return; }
+    }
     int len = min(min(Bmax, g.T0 + 1), wm + 1);  // words computed per column -- warp-uniform (shared code path)
     if (BT > 0) len = min(BT, BT - ((BT - len) / STEP) * STEP);
 #pragma unroll
@@ -230,7 +246,6 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
     // row that is only reachable horizontally) grows by exactly +1 per column, so D'[32*base][c] =
     // topoff + c and every other score is a popcount sum below it -- nothing to track per column.
     int topoff = 0;
-    bool alive = on;
     status = PASS_DEAD;
     score = 0;
     const uint32_t lomask = ((m - 1) & 31) == 31 ? 0xFFFFFFFFu : ((2u << ((m - 1) & 31)) - 1u);  // rows <= m in that word
@@ -279,11 +294,11 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
         int ntop = base, need = 0;
         if (alive) {
             int fa = 0x7FFFFFFF, la = -1;
-            int H = 0;  // absent seeds wholly right of column c
-            {
-                const int s0 = (c + kSeedQ - 1) / kSeedQ, j = s0 >> 3;
-                if (j < sl.J) { const uint32_t v = sl.hs[32 * j]; H = (int)(v & 255u) + __popc((v >> 8) >> (s0 & 7)); }
-            }
+            const int H = seeds_right_of(c);  // absent seeds wholly right of column c
+            // seed band: a path through (r, c') costs >= |r - c'| before the cell and >= H(c') after it, so rows
+            // above c' - (k - H(c')) are never on a path of cost <= k; H shrinks with c': columns (c, c+32] use
+            // H(c+32).  Only the TOP is clipped with it (see the bottom rule above).
+            const int Dc = min(Dl, k - seeds_right_of(c + 32));
             const int rstar = m - (n - c);
             int bst = topoff + c;  // score on the boundary above word t
 #pragma unroll
@@ -305,7 +320,8 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
             if (fa == 0x7FFFFFFF) la = -1;
             if (la >= 0) {
                 // next block: [first strongly alive, last weakly alive + 1], clipped to the rows its columns c+1..c+32 can use
-                ntop = max(base + fa, (c - Dl) > 0 ? (c - Dl) >> 5 : 0);
+                // (Ukkonen's band intersected with the seed band)
+                ntop = max(base + fa, (c - Dc) > 0 ? (c - Dc) >> 5 : 0);
                 const int nbot = min(base + la + 1, min(wm, (c + 31 + El) >> 5));
                 // row 0 (D[0][c] = c) is a boundary, not a word: a path leaving it inside the next block enters
                 // word 0 -- keep word 0 while the row-0 cell itself can be on a path of cost <= k

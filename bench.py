@@ -35,7 +35,7 @@ from amplicon_sorter_b200 import host, synth, thresholds  # noqa: E402
 METRIC = "read-pair comparisons/sec (all-vs-all, ~1 kb reads)"
 UNIT = "pairs/s"
 ALU_OPS_PER_WORD_UPDATE = 10  # ALU-pipe instructions per Myers word-update in asb_screen's SASS (profiles/)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 23.3e6  # dram__bytes_read+write.sum of one asb_screen launch (ncu --set full, profiles/)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 48.7e6  # dram__bytes_read+write.sum of one asb_screen launch (ncu --set full, profiles/r1_asb_screen_ncu_full_v7.txt)
 
 
 def make_workload(n_reads: int):
@@ -325,7 +325,7 @@ def main():
                     "word_updates_per_s": wu_rate, "alu_ops_per_word_update": ALU_OPS_PER_WORD_UPDATE,
                     "word_updates_per_pair": agg["word_updates"] / max(agg["pairs"], 1),
                     "peak_source": "asb_int_peak measured live on this GPU: best of LOP3-chain probe (%.2f) and LOP3/SHF/IADD3/LEA mix probe (%.2f); nominal 148 SM x 64 lanes x 1.965 GHz = 18.61" % (lop3, mix),
-                    "ncu": "profiles/r1_asb_screen_ncu_full_v6.txt: sm__inst_executed_pipe_alu 93.0 % of peak, dram 23.3 MB per launch",
+                    "ncu": "profiles/r1_asb_screen_ncu_full_v7.txt: sm__inst_executed_pipe_alu 91.4 % of peak, dram 48.7 MB per launch",
                     "nominal": {"ops_per_job": nominal_ops(w), "note": "SURVEY 8(d): 20*ceil(m/32)*n*2 per pair (full-matrix Myers, both strands)",
                                 "equivalent_tops": nominal_ops(w) * a.steps / t_res / 1e12 / max(world, 1)},
                     "hbm": {"peak_gbs": _measured_peak("hbm_gbs"), "note": "path is not HBM-bound: ~200 MB of symbol codes stay L2-resident"}}
