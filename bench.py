@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 from amplicon_sorter_b200 import host, synth, thresholds  # noqa: E402
 
+_OUT = sys.stdout
 METRIC = "read-pair comparisons/sec (all-vs-all, ~1 kb reads)"
 UNIT = "pairs/s"
 ALU_OPS_PER_WORD_UPDATE = 10  # ALU-pipe instructions per Myers word-update in asb_screen's SASS (profiles/)
@@ -162,7 +163,7 @@ def run_reference_arm(a):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 def main():
@@ -176,6 +177,12 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): everything else any library prints to fd 1 -- NCCL's
+    # "NCCL version ..." banner under NCCL_DEBUG=VERSION/WARN for one -- is sent to stderr
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         return run_reference_arm(a)
 
@@ -193,8 +200,6 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line ("NCCL version ..." goes to stdout)
         dist.init_process_group("nccl", device_id=dev)
 
     w = make_workload(a.reads)
@@ -340,7 +345,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline}
         if not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(w, seconds=a.cpu_seconds) if world == 1 else None
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
