@@ -33,7 +33,8 @@ _LIB = None
 
 SYMBOLS = ["asb_version", "asb_create", "asb_destroy", "asb_last_error", "asb_set_param", "asb_upload_reads",
            "asb_batch_begin", "asb_batch_step", "asb_batch_records", "asb_distance_pairs", "asb_debug_read", "asb_batch_records_dev", "asb_int_peak", "asb_format_records",
-           "asb_kmer_build", "asb_kmer_shared_pairs", "asb_kmer_shared_tile", "asb_threeway_pairs"]
+           "asb_kmer_build", "asb_kmer_shared_pairs", "asb_kmer_shared_tile", "asb_threeway_pairs",
+           "asb_lines_upload", "asb_lines_hist", "asb_lines_besthit", "asb_lines_besthit_fetch", "asb_components"]
 
 
 def lib_path() -> str:
@@ -72,6 +73,12 @@ def load():
     L.asb_kmer_shared_tile.argtypes = [vp, u32p, C.c_uint32, u32p, C.c_uint32, u32p]
     L.asb_threeway_pairs.argtypes = [vp, u32p, u32p, C.c_uint64, u32p, u32p, C.c_uint32, C.POINTER(StepInfo)]
     L.asb_debug_read.argtypes = [vp, C.c_uint32, C.c_int, u8p, C.c_uint32]
+    fp = C.POINTER(C.c_float)
+    L.asb_lines_upload.argtypes = [vp, u32p, u32p, u32p, C.c_uint64]
+    L.asb_lines_hist.argtypes = [vp, u64p, fp]
+    L.asb_lines_besthit.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u64p, fp]
+    L.asb_lines_besthit_fetch.argtypes = [vp, u32p, u32p]
+    L.asb_components.argtypes = [vp, u32p, u32p, C.c_uint64, C.c_uint32, u32p, fp]
     _LIB = L
     return L
 

@@ -623,6 +623,9 @@ struct asb_ctx {
     bool seeds_ready = false; int seed_lb = 1;
     DevBuf<uint64_t> d_roff_all; DevBuf<uint32_t> d_rlen_all;
     DevBuf<asb_record> d_rec;
+    // lines of <stem>_compare.tmp in integer form (lines.cuh) and the last best-hit result
+    DevBuf<uint32_t> d_la, d_lb, d_lm, d_bh_pos, d_bh_key, d_bh_alt, d_bh_alt2, d_bh_line, d_bh_first;
+    uint64_t n_lines = 0, bh_n = 0; uint32_t lines_max_idx = 0;
 };
 
 namespace {
@@ -835,6 +838,8 @@ void asb_destroy(asb_ctx* ctx)
     ctx->d_dpass.release(); ctx->d_drev.release(); ctx->d_grp.release(); ctx->d_F.release(); ctx->d_R.release(); ctx->d_Z.release();
     ctx->d_O.release(); ctx->d_alt.release(); ctx->d_Zv.release(); ctx->d_Ov.release(); ctx->d_altv.release(); ctx->d_ctr.release();
     ctx->d_tmp.release(); ctx->d_rec.release(); ctx->d_kbits.release(); ctx->d_roff_all.release(); ctx->d_rlen_all.release();
+    ctx->d_la.release(); ctx->d_lb.release(); ctx->d_lm.release(); ctx->d_bh_pos.release(); ctx->d_bh_key.release(); ctx->d_bh_alt.release();
+    ctx->d_bh_alt2.release(); ctx->d_bh_line.release(); ctx->d_bh_first.release();
     ctx->d_qbits.release(); ctx->d_seed_off.release(); ctx->d_order.release(); ctx->d_seeds_f.release(); ctx->d_seeds_r.release(); ctx->d_base2.release();
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1390,3 +1395,5 @@ int asb_distance_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const
 }
 
 }  // extern "C"
+
+#include "lines.cuh"

@@ -126,6 +126,45 @@ class Engine:
                                                  ptr(drev, C.c_uint32), dpass.shape[0], C.byref(info)))
         return self.batch_records(info.n_records), info.as_dict()
 
+    # -- consumers of <stem>_compare.tmp on integer lines (SSG, best-hit filter, grouping) -----------------
+    def lines_upload(self, a, b, milli):
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        milli = np.ascontiguousarray(milli, dtype=np.uint32)
+        self._check(self._lib.asb_lines_upload(self._h, ptr(a, C.c_uint32), ptr(b, C.c_uint32), ptr(milli, C.c_uint32), a.shape[0]))
+        self._lines_token = None
+
+    def lines_hist(self):
+        """(hist[1001] of iden*1000 over the resident lines, device ms)."""
+        hist = np.zeros(1001, dtype=np.uint64)
+        ms = C.c_float()
+        self._check(self._lib.asb_lines_hist(self._h, ptr(hist, C.c_uint64), C.byref(ms)))
+        return hist, ms.value
+
+    def lines_besthit(self, min_milli: int = 0, member_bits=None):
+        """(surviving line numbers, first admitted line of each survivor's key, device ms); key-ascending, list order."""
+        n, ms = C.c_uint64(), C.c_float()
+        mp, mw = None, 0
+        if member_bits is not None:
+            member_bits = np.ascontiguousarray(member_bits, dtype=np.uint32)
+            mp, mw = ptr(member_bits, C.c_uint32), member_bits.shape[0]
+        self._check(self._lib.asb_lines_besthit(self._h, int(min_milli), mp, mw, C.byref(n), C.byref(ms)))
+        line = np.empty(n.value, dtype=np.uint32)
+        first = np.empty(n.value, dtype=np.uint32)
+        if n.value:
+            self._check(self._lib.asb_lines_besthit_fetch(self._h, ptr(line, C.c_uint32), ptr(first, C.c_uint32)))
+        return line, first, ms.value
+
+    def components(self, a, b, n_nodes: int):
+        """(label[n_nodes] = smallest node id of the node's component, device ms)."""
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        label = np.empty(max(int(n_nodes), 1), dtype=np.uint32)
+        ms = C.c_float()
+        self._check(self._lib.asb_components(self._h, ptr(a, C.c_uint32), ptr(b, C.c_uint32), a.shape[0], int(n_nodes),
+                                             ptr(label, C.c_uint32), C.byref(ms)))
+        return label[: int(n_nodes)], ms.value
+
     # -- k-mer side output (new; no reference counterpart) --------------------------------------------
     def kmer_build(self, k: int = 6):
         self._check(self._lib.asb_kmer_build(self._h, int(k)))

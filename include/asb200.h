@@ -125,6 +125,27 @@ int asb_kmer_shared_pairs(asb_ctx *ctx, const uint32_t *a, const uint32_t *b, ui
 int asb_kmer_shared_tile(asb_ctx *ctx, const uint32_t *rows, uint32_t nr, const uint32_t *cols, uint32_t nc,
                          uint32_t *out);
 
+/* ---- "next" rows 3 and 4 of the scope table: the consumers of <stem>_compare.tmp, on the integer form of its
+ * lines.  Line p (FILE ORDER) = fields 0..2 of line.split(':'): a[p] = idx of the shorter read, b[p] = idx of the
+ * longer read (the dictionary key of the reference's filters), milli[p] = iden * 1000 (0..1000; iden has <= 3
+ * decimals, so this is exact and order-preserving).  The lines stay resident until the next upload. */
+int asb_lines_upload(asb_ctx *ctx, const uint32_t *a, const uint32_t *b, const uint32_t *milli, uint64_t n);
+/* Replaces the scan of SSG (:816-826): hist[m] = number of lines with iden*1000 == m (1001 bins).  The host
+ * finishes the estimate with the reference's own float expressions (:828-835). */
+int asb_lines_hist(asb_ctx *ctx, uint64_t *hist, float *device_ms);
+/* Replaces the best-hit filter of update_list (:986-1008; min_milli = 0, member_bits = NULL) and read_indexes
+ * (:1364-1390; a line is admitted iff milli >= min_milli and bit a or bit b of member_bits is set, :1368-1369),
+ * including the order-dependent leftovers of the reference's append/sort/drop loop.  *n_out = surviving lines;
+ * asb_lines_besthit_fetch copies, for every survivor in (key ascending, position in the key's list) order,
+ * its line number and the line number of the key's first admitted line (= dictionary insertion order). */
+int asb_lines_besthit(asb_ctx *ctx, uint32_t min_milli, const uint32_t *member_bits, uint32_t member_words,
+                      uint64_t *n_out, float *device_ms);
+int asb_lines_besthit_fetch(asb_ctx *ctx, uint32_t *out_line, uint32_t *out_first);
+/* Replaces greedy grouping + merge_groups (:1022-1033, :1057-1086), whose fixed point is the connected components
+ * of the best-hit graph: label[v] = smallest node id of v's component (label[v] = v for untouched nodes). */
+int asb_components(asb_ctx *ctx, const uint32_t *a, const uint32_t *b, uint64_t n_edges, uint32_t n_nodes,
+                   uint32_t *label, float *device_ms);
+
 /* Introspection for tests: symbol codes of read r (forward or compl_reverse) as the device holds
  * them, translated back to ASCII. */
 int asb_debug_read(asb_ctx *ctx, uint32_t read, int strand, uint8_t *dst, uint32_t cap);

@@ -548,3 +548,69 @@ int64_t asref_nw_path(const uint8_t *q, int32_t m, const uint8_t *t, int32_t n, 
     free(D);
     return len;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Consumers of <stem>_compare.tmp on integer lines.  Line p = (a[p], b[p],
+ * milli[p] = iden*1000) in file order.
+ *
+ * asref_besthit: the filter of update_list AS:986-1008 / read_indexes AS:1364-1390, statement by
+ * statement: per key b, append the line, stable-sort the key's list ascending by score, drop every
+ * entry whose successor has a strictly higher score.  Output, per key in ascending key order: the
+ * surviving line numbers in list order, and for each the key's first admitted line number.
+ * A line is admitted iff milli >= min_milli and (member == NULL or bit a or bit b is set) AS:1368-1369.
+ * Returns the number of survivors, or -1 on allocation failure.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { uint32_t *line; uint32_t n, cap, first; } bh_list;
+
+int64_t asref_besthit(const uint32_t *a, const uint32_t *b, const uint32_t *milli, uint64_t n, uint32_t min_milli,
+                      const uint32_t *member, uint32_t n_keys, uint32_t *out_line, uint32_t *out_first)
+{
+    bh_list *L = (bh_list *)calloc(n_keys ? n_keys : 1, sizeof(bh_list));
+    if (!L) return -1;
+    for (uint64_t p = 0; p < n; ++p) {
+        if (milli[p] < min_milli) continue;
+        if (member && !(((member[a[p] >> 5] >> (a[p] & 31)) | (member[b[p] >> 5] >> (b[p] & 31))) & 1u)) continue;
+        bh_list *l = &L[b[p]];
+        if (l->n == l->cap) {
+            uint32_t cap = l->cap ? 2 * l->cap : 4;
+            uint32_t *nl = (uint32_t *)realloc(l->line, sizeof(uint32_t) * cap);
+            if (!nl) return -1;
+            l->line = nl; l->cap = cap;
+        }
+        if (l->n == 0) l->first = (uint32_t)p;
+        /* append + stable sort ascending by score: the new entry goes behind its equals */
+        uint32_t k = l->n++;
+        while (k > 0 && milli[l->line[k - 1]] > milli[p]) { l->line[k] = l->line[k - 1]; --k; }
+        l->line[k] = (uint32_t)p;
+        /* drop every entry that is strictly lower than its successor */
+        uint32_t w = 0;
+        for (uint32_t i = 0; i < l->n; ++i)
+            if (i + 1 == l->n || !(milli[l->line[i]] < milli[l->line[i + 1]])) l->line[w++] = l->line[i];
+        l->n = w;
+    }
+    int64_t o = 0;
+    for (uint32_t key = 0; key < n_keys; ++key) {
+        for (uint32_t i = 0; i < L[key].n; ++i) { out_line[o] = L[key].line[i]; out_first[o] = L[key].first; ++o; }
+        free(L[key].line);
+    }
+    free(L);
+    return o;
+}
+
+/* Connected components by plain union-find: label[v] = smallest node id of v's component. */
+static uint32_t uf_root(uint32_t *parent, uint32_t x)
+{
+    while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+    return x;
+}
+
+void asref_components(const uint32_t *a, const uint32_t *b, uint64_t n_edges, uint32_t n_nodes, uint32_t *label)
+{
+    for (uint32_t v = 0; v < n_nodes; ++v) label[v] = v;
+    for (uint64_t e = 0; e < n_edges; ++e) {
+        uint32_t x = uf_root(label, a[e]), y = uf_root(label, b[e]);
+        if (x == y) continue;
+        if (x < y) label[y] = x; else label[x] = y;
+    }
+    for (uint32_t v = 0; v < n_nodes; ++v) label[v] = uf_root(label, v);
+}

@@ -53,6 +53,10 @@ def lib():
         L.asref_kmer_shared.restype = C.c_uint32
         L.asref_nw_path.argtypes = [C.c_char_p, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_char_p, i32p]
         L.asref_nw_path.restype = C.c_int64
+        L.asref_besthit.argtypes = [u32p, u32p, u32p, C.c_uint64, C.c_uint32, u32p, C.c_uint32, u32p, u32p]
+        L.asref_besthit.restype = C.c_int64
+        L.asref_components.argtypes = [u32p, u32p, C.c_uint64, C.c_uint32, u32p]
+        L.asref_components.restype = None
         _LIB = L
     return _LIB
 
@@ -258,3 +262,101 @@ def py_iden_consensus(todolist):
         if idenlist[0] >= 0.60:
             lines.append(str(y) + "," + str(z) + "," + str(idenlist[0]))
     return lines
+
+
+# ----------------------------------------------------------------------------------------------
+# Consumers of <stem>_compare.tmp.
+# ----------------------------------------------------------------------------------------------
+def besthit(a, b, milli, min_milli=0, member_bits=None):
+    """asref_besthit -> (line numbers, first admitted line of each survivor's key); key-ascending, list order."""
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    b = np.ascontiguousarray(b, dtype=np.uint32)
+    milli = np.ascontiguousarray(milli, dtype=np.uint32)
+    n = a.shape[0]
+    n_keys = int(max(a.max(initial=0), b.max(initial=0))) + 1 if n else 1
+    out_line = np.empty(max(n, 1), dtype=np.uint32)
+    out_first = np.empty(max(n, 1), dtype=np.uint32)
+    mp = None
+    if member_bits is not None:
+        member_bits = np.ascontiguousarray(member_bits, dtype=np.uint32)
+        assert member_bits.shape[0] * 32 >= n_keys
+        mp = _p(member_bits, C.c_uint32)
+    r = lib().asref_besthit(_p(a, C.c_uint32), _p(b, C.c_uint32), _p(milli, C.c_uint32), n, int(min_milli), mp, n_keys,
+                            _p(out_line, C.c_uint32), _p(out_first, C.c_uint32))
+    assert r >= 0
+    return out_line[:r].copy(), out_first[:r].copy()
+
+
+def components(a, b, n_nodes):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    b = np.ascontiguousarray(b, dtype=np.uint32)
+    label = np.empty(max(n_nodes, 1), dtype=np.uint32)
+    lib().asref_components(_p(a, C.c_uint32), _p(b, C.c_uint32), a.shape[0], n_nodes, _p(label, C.c_uint32))
+    return label[:n_nodes]
+
+
+def py_ssg(text: str):
+    """SSG AS:809-835 on the text of the file."""
+    totalsimil = 0
+    tempdict = {}
+    for line in text.splitlines():
+        simil = float(line.strip().split(":")[2])
+        tempdict[simil] = tempdict.get(simil, 0) + 1
+        totalsimil += simil
+    templist = sorted(tempdict, reverse=True)
+    b = int(totalsimil * 0.06)
+    N6 = 0
+    for x in templist:
+        N6 += tempdict[x] * x
+        if N6 >= b:
+            return int(x * 100)
+    return None
+
+
+def py_besthit_templist(text: str, ssg=None, indexes=None):
+    """The filter of update_list AS:986-1012 (ssg is None) or read_indexes AS:1364-1398 (ssg = similar_species_groups
+    as a fraction, indexes = set of idx strings) -> the sorted templist of [idxA, idxB, iden] string triples."""
+    tempdict = {}
+    for line in text.splitlines():
+        e = line.strip().split(":")
+        if ssg is None:
+            e = e[:3]
+        elif not (float(e[2]) >= ssg and len({e[0], e[1]}.intersection(indexes)) > 0):
+            continue
+        lst = tempdict.setdefault(e[1], [])
+        lst.append(e)
+        lst.sort(key=lambda x: (int(x[1]), float(x[2])))
+        keep = [x for i, x in enumerate(lst) if i + 1 == len(lst) or not (x[2] < lst[i + 1][2])]
+        lst[:] = keep
+    templist = [x for sub in tempdict.values() for x in sub]
+    if ssg is None:
+        templist.sort(key=lambda x: (float(x[2]), int(x[1])), reverse=True)
+    else:
+        templist.sort(key=lambda x: float(x[2]), reverse=True)
+    return templist
+
+
+def py_groups(templist):
+    """Greedy grouping AS:1022-1031 + merge_groups AS:1057-1086 -> (number of greedy groups, merged groups in order)."""
+    grouplist = []
+    for x in templist:
+        for s in grouplist:
+            if len({x[0], x[1]}.intersection(s)) > 0:
+                s.update({x[0], x[1]})
+                break
+        else:
+            grouplist.append({x[0], x[1]})
+    n_greedy = len(grouplist)
+    if n_greedy > 1:
+        grouplist = [set(g) for g in grouplist if len(g) > 1]
+        a1, a2 = len(grouplist), 0
+        while a1 > a2:
+            a1 = len(grouplist)
+            for p1 in range(len(grouplist) - 1):
+                for p2 in range(p1 + 1, len(grouplist)):
+                    if len(grouplist[p1].intersection(grouplist[p2])) > 0:
+                        grouplist[p1] = grouplist[p1].union(grouplist[p2])
+                        grouplist[p2].clear()
+            grouplist = [g for g in grouplist if len(g) > 0]
+            a2 = len(grouplist)
+    return n_greedy, grouplist

@@ -91,5 +91,20 @@ class OracleEngine:
             out[p] = oracle.hw(x, y) if mode == "HW" else oracle.nw(x, y, "myers")
         return out
 
+    # consumers of <stem>_compare.tmp: the C restatements of oracle/asref.c behind the Engine methods
+    def lines_upload(self, a, b, milli):
+        self._lines = (np.asarray(a, np.uint32), np.asarray(b, np.uint32), np.asarray(milli, np.uint32))
+        self._lines_token = None
+
+    def lines_hist(self):
+        return np.bincount(self._lines[2], minlength=1001).astype(np.uint64), 0.0
+
+    def lines_besthit(self, min_milli=0, member_bits=None):
+        line, first = oracle.besthit(*self._lines, min_milli=min_milli, member_bits=member_bits)
+        return line, first, 0.0
+
+    def components(self, a, b, n_nodes):
+        return oracle.components(a, b, n_nodes), 0.0
+
     def close(self):
         self.closed = True
