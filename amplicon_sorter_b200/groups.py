@@ -153,34 +153,63 @@ def best_hits(engine, lines: Lines, ssg=None, indexes=None, stats: dict | None =
     return templist, a, b, m
 
 
-def make_groups(engine, a, b, stats: dict | None = None):
-    """Greedy grouping (:1022-1031 / :1403-1409) followed by merge_groups (:1057-1086) on the templist edges
-    (a[i], b[i]) in templist order.  Their fixed point is the set of connected components; merge_groups keeps the
-    union at the smaller position, so components are numbered by their first appearance in the templist.
-    Returns (number of groups the greedy pass creates = the 'before merge' count, list of sets of idx strings)."""
-    a = np.ascontiguousarray(a, dtype=np.uint32)
-    b = np.ascontiguousarray(b, dtype=np.uint32)
-    if a.shape[0] == 0:
+def make_groups(engine, templist, update_with_list: bool = False, stats: dict | None = None):
+    """Greedy grouping (:1022-1031 / :1403-1409) followed by merge_groups (:1057-1086) on the templist.
+
+    The fixed point of the two is the set of connected components of the templist edges, numbered by first
+    appearance; the reference gets there with O(groups^2) set intersections, almost all of them between groups of
+    DIFFERENT components, which can never intersect.  The GPU labels the components (asb_components); the host then
+    replays the reference's own set operations -- the same update()/union()/clear() calls on real Python sets, in
+    the same order per set -- only inside each component.  The returned sets therefore have the reference's
+    partition, numbering AND internal layout (iteration order under the same PYTHONHASHSEED), which the later
+    stages depend on (list(set(i)) + random.sample at :1412/:1436).
+    update_with_list: read_indexes grows a group with s.update([x0, x1]) (:1406), update_list with s.update({x0, x1}).
+    Returns (number of groups before merge, merged groups)."""
+    if not templist:
         return 0, []
+    a = np.fromiter((int(x[0]) for x in templist), dtype=np.uint32, count=len(templist))
+    b = np.fromiter((int(x[1]) for x in templist), dtype=np.uint32, count=len(templist))
     n_nodes = int(max(a.max(), b.max())) + 1
     label, ms = engine.components(a, b, n_nodes)
     if stats is not None:
         stats["components_ms"] = ms
-    # greedy creates a group exactly when neither end of an edge has been seen before
-    seq = np.stack([a, b], axis=1).reshape(-1).astype(np.int64)
-    first_seen = np.full(n_nodes, seq.shape[0], dtype=np.int64)
-    np.minimum.at(first_seen, seq, np.arange(seq.shape[0]))
-    e = np.arange(a.shape[0], dtype=np.int64)
-    n_greedy = int(np.count_nonzero((first_seen[a] >= 2 * e) & (first_seen[b] >= 2 * e)))
-    # components in order of first appearance; members = the nodes that occur in an edge
-    lab = label[a].astype(np.int64)
-    roots, first_edge = np.unique(lab, return_index=True)
-    roots = roots[np.argsort(first_edge, kind="stable")]
-    nodes = np.unique(seq)
-    node_lab = label[nodes].astype(np.int64)
-    by = np.argsort(node_lab, kind="stable")
-    nodes, node_lab = nodes[by], node_lab[by]
-    starts = np.searchsorted(node_lab, roots, side="left")
-    ends = np.searchsorted(node_lab, roots, side="right")
-    groups = [set(str(v) for v in nodes[s:t].tolist()) for s, t in zip(starts.tolist(), ends.tolist())]
-    return n_greedy, groups
+    # greedy pass: "the first group that holds x0 or x1" = the lower of the two nodes' first groups
+    grouplist, first = [], {}
+    big = len(templist) + 1
+    for x in templist:
+        x0, x1 = x[0], x[1]
+        g0, g1 = first.get(x0, big), first.get(x1, big)
+        g = g0 if g0 < g1 else g1
+        if g == big:
+            g = len(grouplist)
+            grouplist.append({x0, x1})
+        elif update_with_list:
+            grouplist[g].update([x0, x1])
+        else:
+            grouplist[g].update({x0, x1})
+        if g < g0:
+            first[x0] = g
+        if g < g1:
+            first[x1] = g
+    n_greedy = len(grouplist)
+    if n_greedy <= 1:  # merge_groups leaves a single group alone (:1060)
+        return n_greedy, grouplist
+    grouplist = [i for i in grouplist if len(i) > 1]  # :1063
+    grouplist = [set(i) for i in grouplist]           # :1064
+    buckets: dict = {}
+    for p, g in enumerate(grouplist):
+        buckets.setdefault(int(label[int(next(iter(g)))]), []).append(p)
+    for positions in buckets.values():
+        merged_any = len(positions) > 1
+        while merged_any:  # :1065 `while a1 > a2`: repeat while a pass merged something
+            merged_any = False
+            for i in range(len(positions) - 1):
+                for j in range(i + 1, len(positions)):
+                    pi, pj = positions[i], positions[j]
+                    if not grouplist[pi].isdisjoint(grouplist[pj]):   # :1076
+                        grouplist[pi] = grouplist[pi].union(grouplist[pj])  # :1077
+                        grouplist[pj].clear()                                # :1078
+                        merged_any = True
+            positions[:] = [p for p in positions if len(grouplist[p]) > 0]
+    grouplist = [i for i in grouplist if len(i) > 0]  # :1081
+    return n_greedy, grouplist

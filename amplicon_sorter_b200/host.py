@@ -51,14 +51,17 @@ def _iden_table(lens_sorted: np.ndarray, records: np.ndarray, dcap: np.ndarray |
         dmax = np.zeros(lmax + 1, dtype=np.int64) - 1
         np.maximum.at(dmax, L, d)
     lbase = np.full(lmax + 1, np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
-    strs, soff, n = [], [0], 0
+    strs, soff, n, milli = [], [0], 0, []
     for length in np.nonzero(dmax >= 0)[0].tolist():
         lbase[length] = n
         for dd in range(int(dmax[length]) + 1):
-            t = str(round(1 - dd / length, 3))
+            v = round(1 - dd / length, 3)
+            t = str(v)
             strs.append(t)
             soff.append(soff[-1] + len(t))
+            milli.append(int(round(v * 1000)))  # exact: v has <= 3 decimals
         n += int(dmax[length]) + 1
+    _iden_table.milli = np.asarray(milli, dtype=np.uint32)  # same indexing as the strings (groups.Lines)
     return lbase, np.asarray(soff, dtype=np.uint32), "".join(strs).encode("ascii"), n
 
 
@@ -84,6 +87,9 @@ def format_records(records: np.ndarray, idx_sorted: np.ndarray, lens_sorted: np.
                                C.cast(out, C.c_void_p), cap)
     if k < 0:
         raise RuntimeError(f"asb_format_records failed ({k})")
+    # the same lines in integer form, for the stages that consume the file (groups.py)
+    e = lbase[np.asarray(lens_sorted)[records["j_pos"]].astype(np.int64)].astype(np.int64) + records["d"].astype(np.int64)
+    format_records.last_lines = (idx32[records["i_pos"]], idx32[records["j_pos"]], _iden_table.milli[e], records["reverse"] != 0)
     return out.raw[:k].decode("ascii")
 
 
@@ -175,10 +181,13 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
     for key, rid in idx_to_rid.items():
         rid_to_idx[rid] = key
 
+    from . import groups
+
     ap = AllPairs(engine)
     ap.upload(seqs)
     tl_total = 0
     wrote = False
+    line_parts = []
     for d, rids in zip(self, batch_rids):
         if len(d) == 0:
             continue
@@ -190,6 +199,9 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
             with open(out_path, "a") as f:  # :803
                 f.write(text)
             wrote = True
+            line_parts.append(groups.Lines(*format_records.last_lines))
+    if wrote:  # the consumers of the file (SSG, update_list, read_indexes) get its lines without parsing the text
+        groups.CACHE[os.path.abspath(out_path)] = (groups.Lines.concat(line_parts), os.path.getsize(out_path))
     if stats_out is not None:
         stats_out.update(ap.stats)
         stats_out["tl"] = tl_total

@@ -336,13 +336,14 @@ def py_besthit_templist(text: str, ssg=None, indexes=None):
     return templist
 
 
-def py_groups(templist):
-    """Greedy grouping AS:1022-1031 + merge_groups AS:1057-1086 -> (number of greedy groups, merged groups in order)."""
+def py_groups(templist, update_with_list=False):
+    """Greedy grouping AS:1022-1031 (read_indexes' variant AS:1403-1409 grows a group from a list) + merge_groups
+    AS:1057-1086 -> (number of greedy groups, merged groups in order)."""
     grouplist = []
     for x in templist:
         for s in grouplist:
             if len({x[0], x[1]}.intersection(s)) > 0:
-                s.update({x[0], x[1]})
+                s.update([x[0], x[1]] if update_with_list else {x[0], x[1]})
                 break
         else:
             grouplist.append({x[0], x[1]})

@@ -68,6 +68,10 @@ def main():
 
             ns["do_parallel"] = do_parallel
 
+        if "groups" in os.environ.get("ASB200_STAGES", "groups"):
+            shared = OracleEngine()
+            launcher.install_group_stage(ns, lambda: shared)
+
     inner_pl = ns["process_list"]
     inner_sg = ns["sort_groups"]
 

@@ -38,7 +38,7 @@ st = {}
 for rep in range(2):
     t0 = time.perf_counter(); ssg = groups.ssg_estimate(eng, lines, st); out["ssg_wall_s"] = time.perf_counter() - t0
     t0 = time.perf_counter(); templist, ta, tb, tm = groups.best_hits(eng, lines, stats=st); out["besthit_wall_s"] = time.perf_counter() - t0
-    t0 = time.perf_counter(); n_greedy, grp = groups.make_groups(eng, ta, tb, st); out["groups_wall_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); n_greedy, grp = groups.make_groups(eng, templist, False, st); out["groups_wall_s"] = time.perf_counter() - t0
     members = grp[0]
     t0 = time.perf_counter(); tl2, *_ = groups.best_hits(eng, lines, 0.93, members, stats=None); out["read_indexes_wall_s"] = time.perf_counter() - t0
 out.update(st, ssg=ssg, templist=len(templist), n_greedy=n_greedy, groups=len(grp), read_indexes_templist=len(tl2))

@@ -19,7 +19,7 @@ from oracle import oracle
 from tests.fake_engine import OracleEngine
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.json.gz")))
+FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "g*.json.gz")))
 
 
 def load(path):

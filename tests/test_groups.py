@@ -77,14 +77,17 @@ def check_product(fx, engine):
     assert groups.ssg_estimate(engine, lines) == fx["ssg"]
     templist, a, b, m = groups.best_hits(engine, lines)
     assert templist == fx["update_list"]["templist"]
-    n_greedy, merged = groups.make_groups(engine, a, b)
+    n_greedy, merged = groups.make_groups(engine, templist)
     assert n_greedy == fx["update_list"]["n_greedy"]
     assert as_sorted(merged) == fx["update_list"]["groups"]  # same partition, same numbering
+    # ... and the same set internals as the reference's own sequence of set operations (same process = same hash seed)
+    assert [list(g) for g in merged] == [list(g) for g in oracle.py_groups(templist)[1]]
     for case in fx["read_indexes"]:
         tl, a, b, m = groups.best_hits(engine, lines, case["ssg"] / 100, set(case["members"]))
         assert tl == case["templist"]
-        n_greedy, merged = groups.make_groups(engine, a, b)
+        n_greedy, merged = groups.make_groups(engine, tl, update_with_list=True)
         assert n_greedy == case["n_greedy"] and as_sorted(merged) == case["groups"]
+        assert [list(g) for g in merged] == [list(g) for g in oracle.py_groups(tl, update_with_list=True)[1]]
 
 
 @pytest.mark.parametrize("path", FIXTURES, ids=IDS)
