@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? 4 : 1) asb_screen(c
         if (lane == 0) t = atomicAdd(&B.ctr[C_TASK], 1ull);
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
         if (t >= B.n_tasks) break;
-        const uint32_t gidx = (uint32_t)t * B.world + B.rank;  // cyclic deal of groups over ranks
+        const uint32_t gidx = (uint32_t)t * B.world + B.rank;  // (world, rank) = (1, 0): the host deals whole rows
         // row = last r with grp_prefix[r] <= gidx
         uint32_t lo = 0, hi = B.rows;
         while (hi - lo > 1) {
@@ -1036,7 +1036,11 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     if (n == 0 || r0 >= n) { ctx->next_row = n; ctx->rec_n = 0; return ASB_DONE; }
     // slab: rows of one window class, at most pair_cap pairs
     const int cls = class_for(std::min(need_words(ctx, r0, ctx->h_pmax_dpass, 0), (int)((ctx->h_len[r0] + 31) / 32)));
-    uint64_t pairs = 0, groups = 0;
+    // Rows are dealt to the ranks cyclically (row p belongs to rank p % world): a rank then sees whole rows, so the
+    // row-runs of its sorted lists are as long as on a single GPU (dealing 32-target groups instead left 1/world of
+    // every row on each rank and the list warps mostly empty at 8 GPUs).  Neighbouring rows have almost the same
+    // number of partners, so the shares differ by O(n) pairs of O(n^2 / world).
+    uint64_t pairs = 0, groups = 0, my_pairs = 0;
     uint32_t r1 = r0;
     int zneed = 0;
     uint32_t wmax = 1;
@@ -1053,7 +1057,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
             wmax = std::max<uint32_t>(wmax, (uint32_t)W);
         }
         pairs += cnt;
-        groups += (cnt + 31) / 32;
+        if (r1 % ctx->world == ctx->rank) { groups += (cnt + 31) / 32; my_pairs += cnt; }
         if (groups > 0xFFFFFFF0ull) return fail(ctx, ASB_E_ARG, "pair_cap too large for 32-bit group indices");
         prefix.push_back((uint32_t)groups);
         ++r1;
@@ -1061,8 +1065,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     const int zcls = class_for(zneed);
     int rc = ensure_seeds(ctx);
     if (rc) return rc;
-    // this rank owns every world-th group: at most ceil(groups/world) groups of 32 pairs
-    const uint64_t cap = std::max<uint64_t>(std::min<uint64_t>(pairs, ((groups + ctx->world - 1) / ctx->world) * 32), 32);
+    const uint64_t cap = std::max<uint64_t>(my_pairs, 32);
     rc = ensure_lists(ctx, cap);
     if (rc) return rc;
     CU(ctx->d_grp.ensure(prefix.size()));
@@ -1076,8 +1079,8 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
     B.ctr = ctx->d_ctr.p; B.list_cap = ctx->list_cap;
     B.grp_prefix = ctx->d_grp.p; B.row_begin = r0; B.rows = r1 - r0;
-    B.rank = ctx->rank; B.world = ctx->world;
-    B.n_tasks = groups > ctx->rank ? (uint32_t)((groups - ctx->rank + ctx->world - 1) / ctx->world) : 0;
+    B.rank = 0; B.world = 1;  // grp_prefix already holds this rank's rows only
+    B.n_tasks = (uint32_t)groups;
     B.screen_cols_num = std::max(1, (int)(ctx->screen_frac * 256.0 + 0.5));
     B.push_thresh = ctx->push_thresh;
     B.cont_thresh = ctx->cont_thresh;
@@ -1108,22 +1111,6 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); info->screen_ms = ms;
     CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2])); info->total_ms = ms;
-    // pairs owned by this rank: groups dealt cyclically
-    uint64_t my_pairs = 0;
-    if (ctx->world == 1) my_pairs = pairs;
-    else {
-        const uint64_t Wd = ctx->world, rk = ctx->rank;
-        for (uint32_t r = r0; r < r1; ++r) {
-            const uint64_t cnt = ctx->h_hi[r] - r, g0 = prefix[r - r0], g1 = prefix[r - r0 + 1];
-            if (g1 == g0) continue;
-            // groups g in [g0,g1) with g % world == rank
-            const uint64_t first = g0 + ((rk + Wd - g0 % Wd) % Wd);
-            if (first >= g1) continue;
-            const uint64_t mine = (g1 - 1 - first) / Wd + 1;
-            my_pairs += 32 * mine;
-            if ((g1 - 1) % Wd == rk) my_pairs -= 32 * (g1 - g0) - cnt;  // the row's last group is partial
-        }
-    }
     info->pairs = my_pairs;
     info->row_begin = r0; info->row_end = r1;
     info->launches = ctx->launches;

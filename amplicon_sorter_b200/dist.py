@@ -1,7 +1,7 @@
 """One process per GPU: shard the all-pairs stage over ranks with torch.distributed.
 
 The pair set shards with no exchange step: every rank holds all reads and
-decides the 32-target groups `gidx % world == rank` of every row.  The only communication is
+decides the rows `p % world == rank` of the sorted batch.  The only communication is
 (1) rank 0 broadcasting the job (reads + batch composition) to the workers and (2) the gather of
 the compacted per-rank record lists to rank 0 -- NCCL over NVLink on GPUs, gloo in CPU tests.
 

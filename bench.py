@@ -341,7 +341,7 @@ def main():
                            "reads": w["n_reads"], "pairs_per_step": w["tl"], "records_per_step": n_records, "mean_read_len": w["mean_len"],
                            "l2_policy": ("inputs (2 x %.0f MB symbol codes) exceed the 126 MB L2; no flush needed" % (w["buf"].nbytes / 1e6)) if flush_buf is None
                            else "inputs fit in L2: a 192 MB buffer is overwritten between timed steps",
-                           "sharding": "32-target groups of every row dealt cyclically over ranks; NCCL gather of records to rank 0"},
+                           "sharding": "rows of the length-sorted batch dealt cyclically over ranks; NCCL gather of records to rank 0"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline}
         if not a.no_cpu:
             line["cpu_baseline"] = cpu_baseline(w, seconds=a.cpu_seconds) if world == 1 else None

@@ -76,7 +76,7 @@ int asb_upload_reads(asb_ctx *ctx, const uint8_t *ascii, const uint64_t *offs, u
  * length-sorted order of :669; hi[p] = last position j kept by the window test :679 for row p
  * (hi[p] >= p; hi[p] == p means no partner); dpass/drev[L] = integer cut-offs for a longer read
  * of length L (see thresholds.py): pass iff d <= dpass[L]; retry on compl_reverse iff d >= drev[L].
- * (rank, world) shards the 32-target groups of every row cyclically; a single GPU is (0, 1). */
+ * (rank, world) shards the rows cyclically (row p of the sorted batch belongs to rank p % world); a single GPU is (0, 1). */
 int asb_batch_begin(asb_ctx *ctx, const uint32_t *order, uint32_t n, const uint32_t *hi,
                     const uint32_t *dpass, const uint32_t *drev, uint32_t table_len,
                     uint32_t rank, uint32_t world);

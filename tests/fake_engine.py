@@ -30,12 +30,9 @@ class OracleEngine:
             cnt = int(hi[i]) - i
             if cnt <= 0:
                 continue
-            js = np.arange(i + 1, int(hi[i]) + 1)
-            grp = g + (js - (i + 1)) // 32
-            g += (cnt + 31) // 32
-            js = js[grp % world == rank]
-            if js.size == 0:
+            if i % world != rank:  # rows are dealt cyclically, like the engine does
                 continue
+            js = np.arange(i + 1, int(hi[i]) + 1)
             pairs += js.size
             a = np.full(js.size, order[i], dtype=np.uint32)
             b = order[js]
