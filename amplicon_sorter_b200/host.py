@@ -61,24 +61,26 @@ def _iden_table(lens_sorted: np.ndarray, records: np.ndarray, dcap: np.ndarray |
             soff.append(soff[-1] + len(t))
             milli.append(int(round(v * 1000)))  # exact: v has <= 3 decimals
         n += int(dmax[length]) + 1
-    _iden_table.milli = np.asarray(milli, dtype=np.uint32)  # same indexing as the strings (groups.Lines)
-    return lbase, np.asarray(soff, dtype=np.uint32), "".join(strs).encode("ascii"), n
+    return lbase, np.asarray(soff, dtype=np.uint32), "".join(strs).encode("ascii"), n, np.asarray(milli, dtype=np.uint32)
 
 
-def format_records(records: np.ndarray, idx_sorted: np.ndarray, lens_sorted: np.ndarray, dcap: np.ndarray | None = None) -> str:
+def format_records(records: np.ndarray, idx_sorted: np.ndarray, lens_sorted: np.ndarray, dcap: np.ndarray | None = None,
+                   with_lines: bool = False):
     """Records -> the lines of amplicon_sorter.py:792-798: 'idxA:idxB:iden' or '...:reverse'.
-    Text assembly runs in the library's host-side C (asb_format_records); the iden strings are Python's."""
+    Text assembly runs in the library's host-side C (asb_format_records); the iden strings are Python's.
+    with_lines: also return the same lines in integer form (idxA, idxB, iden*1000, reverse flag) for groups.Lines."""
     import ctypes as C
 
     from . import _ffi
 
     n = int(records.shape[0])
     if n == 0:
-        return ""
+        z = np.zeros(0, dtype=np.uint32)
+        return ("", (z, z, z, z.astype(bool))) if with_lines else ""
     records = np.ascontiguousarray(records)
     idx32 = np.ascontiguousarray(idx_sorted, dtype=np.uint32)
     len32 = np.ascontiguousarray(lens_sorted, dtype=np.uint32)
-    lbase, soff, sbuf, nstr = _iden_table(np.asarray(lens_sorted), records, dcap)
+    lbase, soff, sbuf, nstr, milli = _iden_table(np.asarray(lens_sorted), records, dcap)
     cap = n * (32 + 8) + 64
     out = C.create_string_buffer(cap)
     lib = _ffi.load()
@@ -87,10 +89,11 @@ def format_records(records: np.ndarray, idx_sorted: np.ndarray, lens_sorted: np.
                                C.cast(out, C.c_void_p), cap)
     if k < 0:
         raise RuntimeError(f"asb_format_records failed ({k})")
-    # the same lines in integer form, for the stages that consume the file (groups.py)
+    text = out.raw[:k].decode("ascii")
+    if not with_lines:
+        return text
     e = lbase[np.asarray(lens_sorted)[records["j_pos"]].astype(np.int64)].astype(np.int64) + records["d"].astype(np.int64)
-    format_records.last_lines = (idx32[records["i_pos"]], idx32[records["j_pos"]], _iden_table.milli[e], records["reverse"] != 0)
-    return out.raw[:k].decode("ascii")
+    return text, (idx32[records["i_pos"]], idx32[records["j_pos"]], milli[e], records["reverse"] != 0)
 
 
 class AllPairs:
@@ -195,11 +198,12 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
         d[:] = [d[i] for i in perm.tolist()]  # side effect (1): batch left length-sorted in place
         tl_total += tl
         if tl:
-            text = format_records(recs, rid_to_idx[order.astype(np.int64)], lens_sorted, getattr(ap, "last_dpass", None))
+            text, ints = format_records(recs, rid_to_idx[order.astype(np.int64)], lens_sorted, getattr(ap, "last_dpass", None),
+                                        with_lines=True)
             with open(out_path, "a") as f:  # :803
                 f.write(text)
             wrote = True
-            line_parts.append(groups.Lines(*format_records.last_lines))
+            line_parts.append(groups.Lines(*ints))
     if wrote:  # the consumers of the file (SSG, update_list, read_indexes) get its lines without parsing the text
         groups.CACHE[os.path.abspath(out_path)] = (groups.Lines.concat(line_parts), os.path.getsize(out_path))
     if stats_out is not None:

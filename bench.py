@@ -293,10 +293,11 @@ def main():
     # ---- end-to-end arm: host buffers in, merged records out, every step ------------------------
     e2e = None
     if a.e2e_steps > 0:
+        # pinned destination of the result, sized from the resident arm's record count (buffer set-up, like the pinned inputs)
+        host_pin = torch.empty((max(n_records, 1), 4), dtype=torch.int32).pin_memory() if rank == 0 else None
         barrier()
         t0 = time.perf_counter()
         d2h = 0
-        host_pin = None
         for _ in range(a.e2e_steps):
             eng.upload_reads(h_buf, h_offs)
             out = job()
