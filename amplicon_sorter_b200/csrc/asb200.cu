@@ -601,6 +601,7 @@ struct asb_ctx {
     std::vector<uint64_t> h_roff;  // [n_reads+1] padded code offsets
     std::vector<uint32_t> h_rlen;
     DevBuf<uint8_t> d_cf, d_cr;
+    DevBuf<uint8_t> d_up_ascii, d_up_maps; DevBuf<uint64_t> d_up_offs, d_up_roff; DevBuf<uint32_t> d_up_present;  // upload staging
     // batch
     uint32_t n = 0, rank = 0, world = 1, table_len = 0;
     std::vector<uint32_t> h_len, h_hi, h_dpass, h_drev;
@@ -626,6 +627,7 @@ struct asb_ctx {
     // lines of <stem>_compare.tmp in integer form (lines.cuh) and the last best-hit result
     DevBuf<uint32_t> d_la, d_lb, d_lm, d_bh_pos, d_bh_key, d_bh_alt, d_bh_alt2, d_bh_line, d_bh_first;
     uint64_t n_lines = 0, bh_n = 0; uint32_t lines_max_idx = 0;
+    DevBuf<uint32_t> d_s_u32[7]; DevBuf<int32_t> d_s_i32[2]; DevBuf<uint8_t> d_s_flag; DevBuf<unsigned long long> d_s_hist;  // scratch of lines.cuh
 };
 
 namespace {
@@ -838,6 +840,10 @@ void asb_destroy(asb_ctx* ctx)
     ctx->d_dpass.release(); ctx->d_drev.release(); ctx->d_grp.release(); ctx->d_F.release(); ctx->d_R.release(); ctx->d_Z.release();
     ctx->d_O.release(); ctx->d_alt.release(); ctx->d_Zv.release(); ctx->d_Ov.release(); ctx->d_altv.release(); ctx->d_ctr.release();
     ctx->d_tmp.release(); ctx->d_rec.release(); ctx->d_kbits.release(); ctx->d_roff_all.release(); ctx->d_rlen_all.release();
+    for (auto& b : ctx->d_s_u32) b.release();
+    for (auto& b : ctx->d_s_i32) b.release();
+    ctx->d_s_flag.release(); ctx->d_s_hist.release();
+    ctx->d_up_ascii.release(); ctx->d_up_maps.release(); ctx->d_up_offs.release(); ctx->d_up_roff.release(); ctx->d_up_present.release();
     ctx->d_la.release(); ctx->d_lb.release(); ctx->d_lm.release(); ctx->d_bh_pos.release(); ctx->d_bh_key.release(); ctx->d_bh_alt.release();
     ctx->d_bh_alt2.release(); ctx->d_bh_line.release(); ctx->d_bh_first.release();
     ctx->d_qbits.release(); ctx->d_seed_off.release(); ctx->d_order.release(); ctx->d_seeds_f.release(); ctx->d_seeds_r.release(); ctx->d_base2.release();
@@ -880,8 +886,9 @@ int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, u
     ctx->kmer_k = 0;
     ctx->seeds_ready = false;
     const uint64_t total = ctx->h_roff[n_reads] + (((uint64_t)max_len + 31) & ~31ull) + 128;  // over-read slack for short lanes
-    DevBuf<uint8_t> d_ascii; DevBuf<uint64_t> d_offs, d_roff; DevBuf<uint32_t> d_present; DevBuf<uint8_t> d_maps;
-    struct Guard { DevBuf<uint8_t>&a; DevBuf<uint64_t>&b,&c; DevBuf<uint32_t>&d; DevBuf<uint8_t>&e; ~Guard(){a.release();b.release();c.release();d.release();e.release();} } guard{d_ascii, d_offs, d_roff, d_present, d_maps};
+    // staging buffers live in the context: a cudaMalloc / cudaFree pair per upload costs more than the upload itself
+    DevBuf<uint8_t>& d_ascii = ctx->d_up_ascii; DevBuf<uint64_t>& d_offs = ctx->d_up_offs; DevBuf<uint64_t>& d_roff = ctx->d_up_roff;
+    DevBuf<uint32_t>& d_present = ctx->d_up_present; DevBuf<uint8_t>& d_maps = ctx->d_up_maps;
     CU(d_ascii.ensure(nbytes + 1)); CU(d_offs.ensure((size_t)n_reads + 1)); CU(d_roff.ensure((size_t)n_reads + 1));
     CU(d_present.ensure(8)); CU(d_maps.ensure(512));
     CU(ctx->d_cf.ensure(total)); CU(ctx->d_cr.ensure(total));

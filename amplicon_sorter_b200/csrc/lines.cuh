@@ -195,8 +195,7 @@ int asb_lines_hist(asb_ctx* ctx, uint64_t* hist, float* device_ms)
 {
     if (!ctx || !hist) return fail(ctx, ASB_E_ARG, "null argument");
     CU(cudaSetDevice(ctx->device));
-    DevBuf<unsigned long long> d_hist;
-    struct Guard { DevBuf<unsigned long long>& a; ~Guard() { a.release(); } } guard{d_hist};
+    DevBuf<unsigned long long>& d_hist = ctx->d_s_hist;  // scratch lives in the context (no cudaMalloc / cudaFree per call)
     CU(d_hist.ensure(asb::kMilliBins));
     CU(cudaMemsetAsync(d_hist.p, 0, sizeof(unsigned long long) * asb::kMilliBins, ctx->stream));
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -221,9 +220,8 @@ int asb_lines_besthit(asb_ctx* ctx, uint32_t min_milli, const uint32_t* member_b
     const uint64_t n = ctx->n_lines;
     if (n == 0) return ASB_OK;
     if (member_bits && (uint64_t)member_words * 32 <= ctx->lines_max_idx) return fail(ctx, ASB_E_ARG, "member bitmap (%u words) does not cover idx %u", member_words, ctx->lines_max_idx);
-    DevBuf<uint32_t> d_member, d_nsel;
-    DevBuf<uint8_t> d_flag;
-    struct Guard { DevBuf<uint32_t>&a,&b; DevBuf<uint8_t>&c; ~Guard() { a.release(); b.release(); c.release(); } } guard{d_member, d_nsel, d_flag};
+    DevBuf<uint32_t>& d_member = ctx->d_s_u32[0]; DevBuf<uint32_t>& d_nsel = ctx->d_s_u32[1];
+    DevBuf<uint8_t>& d_flag = ctx->d_s_flag;
     CU(d_nsel.ensure(1)); CU(d_flag.ensure(n));
     if (member_bits) {
         CU(d_member.ensure(member_words));
@@ -274,10 +272,9 @@ int asb_lines_besthit(asb_ctx* ctx, uint32_t min_milli, const uint32_t* member_b
     CU(cudaMemcpyAsync(&n_seg, d_nsel.p, sizeof n_seg, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     // 4. per-key filter
-    DevBuf<int32_t> d_prev, d_rh;
-    DevBuf<uint32_t> d_rv, d_rc, d_local, d_cnt, d_off;
-    struct Guard2 { DevBuf<int32_t>&a,&b; DevBuf<uint32_t>&c,&d,&e,&f,&g; ~Guard2() { a.release(); b.release(); c.release(); d.release(); e.release(); f.release(); g.release(); } }
-        guard2{d_prev, d_rh, d_rv, d_rc, d_local, d_cnt, d_off};
+    DevBuf<int32_t>& d_prev = ctx->d_s_i32[0]; DevBuf<int32_t>& d_rh = ctx->d_s_i32[1];
+    DevBuf<uint32_t>& d_rv = ctx->d_s_u32[2]; DevBuf<uint32_t>& d_rc = ctx->d_s_u32[3]; DevBuf<uint32_t>& d_local = ctx->d_s_u32[4];
+    DevBuf<uint32_t>& d_cnt = ctx->d_s_u32[5]; DevBuf<uint32_t>& d_off = ctx->d_s_u32[6];
     CU(d_prev.ensure(nq)); CU(d_rh.ensure(nq)); CU(d_rv.ensure(nq)); CU(d_rc.ensure(nq)); CU(d_local.ensure(nq));
     CU(d_cnt.ensure((size_t)n_seg + 1)); CU(d_off.ensure((size_t)n_seg + 1));
     asb::asb_besthit_kernel<<<(n_seg + 127) / 128, 128, 0, ctx->stream>>>(pos_sorted, ctx->d_lm.p, seg_start, n_seg, nq, d_prev.p, d_rv.p, d_rh.p,
@@ -323,8 +320,8 @@ int asb_components(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, uint64_t 
     if (device_ms) *device_ms = 0.f;
     if (n_nodes == 0) return ASB_OK;
     CU(cudaSetDevice(ctx->device));
-    DevBuf<uint32_t> d_a, d_b, d_parent, d_label;
-    struct Guard { DevBuf<uint32_t>&a,&b,&c,&d; ~Guard() { a.release(); b.release(); c.release(); d.release(); } } guard{d_a, d_b, d_parent, d_label};
+    DevBuf<uint32_t>& d_a = ctx->d_s_u32[2]; DevBuf<uint32_t>& d_b = ctx->d_s_u32[3]; DevBuf<uint32_t>& d_parent = ctx->d_s_u32[4];
+    DevBuf<uint32_t>& d_label = ctx->d_s_u32[5];
     CU(d_a.ensure(n_edges)); CU(d_b.ensure(n_edges)); CU(d_parent.ensure(n_nodes)); CU(d_label.ensure(n_nodes));
     if (n_edges) {
         CU(cudaMemcpyAsync(d_a.p, a, sizeof(uint32_t) * n_edges, cudaMemcpyHostToDevice, ctx->stream));

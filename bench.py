@@ -298,22 +298,30 @@ def main():
         barrier()
         t0 = time.perf_counter()
         d2h = 0
+        parts_ms = {"upload": 0.0, "job_and_gather": 0.0, "d2h": 0.0}
         for _ in range(a.e2e_steps):
+            ta = time.perf_counter()
             eng.upload_reads(h_buf, h_offs)
+            tb = time.perf_counter()
             out = job()
+            torch.cuda.synchronize()
+            tc = time.perf_counter()
             if rank == 0:
                 if host_pin is None or host_pin.shape[0] < out.shape[0]:
                     host_pin = torch.empty((max(out.shape[0], 1), 4), dtype=torch.int32).pin_memory()
                 host_pin[: out.shape[0]].copy_(out, non_blocking=True)  # D2H of the merged records into pinned memory
                 torch.cuda.synchronize()
                 d2h = out.numel() * 4
+            td = time.perf_counter()
+            for k, v in zip(parts_ms, (tb - ta, tc - tb, td - tc)):
+                parts_ms[k] += v * 1e3 / a.e2e_steps
         barrier()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         h2d = (h_buf.nbytes + h_offs.nbytes + w["order"].nbytes + w["hi"].nbytes + w["dpass"].nbytes + w["drev"].nbytes) * world
         e2e = {"value": w["tl"] * a.e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": a.e2e_steps,
+               "d2h_bytes_per_step": int(d2h), "steps": a.e2e_steps, "rank0_ms_per_step": {k: round(v, 1) for k, v in parts_ms.items()},
                "api": "asb_upload_reads + asb_batch_begin/step + asb_batch_records_dev + NCCL gather + D2H on rank 0"}
 
     if rank == 0:
