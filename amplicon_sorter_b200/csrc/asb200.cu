@@ -949,12 +949,16 @@ int asb_batch_begin(asb_ctx* ctx, const uint32_t* order, uint32_t n, const uint3
     ctx->n = n; ctx->rank = rank; ctx->world = world; ctx->table_len = table_len;
     ctx->h_len.resize(n); ctx->h_hi.assign(hi, hi + n);
     std::vector<uint64_t> pos_off(n);
+    uint32_t reach = 0;  // last position inside the window of an earlier row
     for (uint32_t p = 0; p < n; ++p) {
         if (order[p] >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "order[%u]=%u is not an uploaded read", p, order[p]);
         ctx->h_len[p] = ctx->h_rlen[order[p]];
         pos_off[p] = ctx->h_roff[order[p]];
-        if (p && ctx->h_len[p] < ctx->h_len[p - 1]) return fail(ctx, ASB_E_ARG, "batch is not sorted by length at position %u", p);
+        // a row's partners must not be shorter than the row (the shorter read is the DP query, :225-230): lengths are
+        // non-decreasing inside every window.  Several length-sorted batches may be laid end to end.
+        if (p && p <= reach && ctx->h_len[p] < ctx->h_len[p - 1]) return fail(ctx, ASB_E_ARG, "batch is not sorted by length at position %u", p);
         if (hi[p] < p || hi[p] >= n) return fail(ctx, ASB_E_ARG, "hi[%u]=%u out of range", p, hi[p]);
+        reach = std::max(reach, hi[p]);
         if (ctx->h_len[p] >= table_len) return fail(ctx, ASB_E_ARG, "read length %u >= table_len %u", ctx->h_len[p], table_len);
     }
     ctx->h_dpass.assign(dpass, dpass + table_len); ctx->h_drev.assign(drev, drev + table_len);

@@ -134,6 +134,39 @@ class AllPairs:
         self.last_dpass = dpass
         return perm, order, lens_sorted, recs, tl
 
+    def compare_many(self, batches_read_ids, similar_genes: float, rank=0, world=1):
+        """All batches of one input file as ONE engine batch: the length-sorted batches are laid end to end
+        (position = batch offset + position in the batch), a row's window never leaves its own batch, and the
+        records come back in (batch, i, j) order -- the order of the reference's file.  A default-mode run is
+        dozens of 1,000-read batches of 0.5 M pairs each; one launch per batch cannot fill 148 SMs.
+        Returns (perms per batch, order, lens_sorted, records with GLOBAL positions, tl)."""
+        perms, orders, lens_all, his = [], [], [], []
+        base = 0
+        for read_ids in batches_read_ids:
+            read_ids = np.asarray(read_ids, dtype=np.int64)
+            lens = self.lens[read_ids]
+            perm = np.argsort(lens, kind="stable")  # d.sort(key=lambda x: len(x[1]))  :669
+            perms.append(perm)
+            orders.append(read_ids[perm].astype(np.uint32))
+            lens_all.append(lens[perm])
+            his.append(batch_geometry(lens[perm]).astype(np.int64) + base)
+            base += read_ids.shape[0]
+        order = np.concatenate(orders) if orders else np.zeros(0, np.uint32)
+        lens_sorted = np.concatenate(lens_all) if lens_all else np.zeros(0, np.int64)
+        hi = (np.concatenate(his) if his else np.zeros(0, np.int64)).astype(np.uint32)
+        tl = int((hi.astype(np.int64) - np.arange(hi.shape[0])).sum())
+        if tl == 0:
+            return perms, order, lens_sorted, np.empty(0, dtype=self._rec_dtype()), 0
+        dpass, drev = thresholds.tables(similar_genes / 100, int(lens_sorted.max()) + 1)  # similarg :783
+        recs, tot = self.engine.compare_batch(order, hi, dpass, drev, rank, world)
+        self.stats["pairs"] += tot["pairs"]
+        self.stats["records"] += tot["n_records"]
+        for k in ("fwd_survivors", "rc_survivors", "zone_checks", "word_updates", "screen_ms"):
+            self.stats[k] += tot[k]
+        self.stats["gpu_ms"] += tot["total_ms"]
+        self.last_dpass = dpass
+        return perms, order, lens_sorted, recs, tl
+
     @staticmethod
     def _rec_dtype():
         from ._ffi import RECORD
@@ -188,22 +221,20 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
 
     ap = AllPairs(engine)
     ap.upload(seqs)
-    tl_total = 0
     wrote = False
     line_parts = []
-    for d, rids in zip(self, batch_rids):
-        if len(d) == 0:
-            continue
-        perm, order, lens_sorted, recs, tl = ap.compare(rids, args.similar_genes)
+    live = [(d, rids) for d, rids in zip(self, batch_rids) if len(d)]
+    perms, order, lens_sorted, recs, tl_total = ap.compare_many([rids for _, rids in live], args.similar_genes)
+    for (d, _), perm in zip(live, perms):
         d[:] = [d[i] for i in perm.tolist()]  # side effect (1): batch left length-sorted in place
-        tl_total += tl
-        if tl:
-            text, ints = format_records(recs, rid_to_idx[order.astype(np.int64)], lens_sorted, getattr(ap, "last_dpass", None),
-                                        with_lines=True)
-            with open(out_path, "a") as f:  # :803
-                f.write(text)
-            wrote = True
-            line_parts.append(groups.Lines(*ints))
+    if tl_total:
+        # records are sorted by (global i, global j) = (batch, i, j): the reference's -np 1 file order
+        text, ints = format_records(recs, rid_to_idx[order.astype(np.int64)], lens_sorted, getattr(ap, "last_dpass", None),
+                                    with_lines=True)
+        with open(out_path, "a") as f:  # :803
+            f.write(text)
+        wrote = True
+        line_parts.append(groups.Lines(*ints))
     if wrote:  # the consumers of the file (SSG, update_list, read_indexes) get its lines without parsing the text
         groups.CACHE[os.path.abspath(out_path)] = (groups.Lines.concat(line_parts), os.path.getsize(out_path))
     if stats_out is not None:

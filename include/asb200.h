@@ -72,8 +72,9 @@ int asb_set_param(asb_ctx *ctx, const char *name, double value);
  * compl_reverse symbol codes in HBM.  Buffers are caller-owned and copied during the call. */
 int asb_upload_reads(asb_ctx *ctx, const uint8_t *ascii, const uint64_t *offs, uint32_t n_reads);
 
-/* Replaces process_list.queuer (:662-715) for one batch.  order[n] = read ids in the stable
- * length-sorted order of :669; hi[p] = last position j kept by the window test :679 for row p
+/* Replaces process_list.queuer (:662-715) for one batch -- or for several batches laid end to end
+ * (a row's window (p, hi[p]] never leaves its batch; lengths must be non-decreasing inside every window).
+ * order[n] = read ids in the stable length-sorted order of :669; hi[p] = last position j kept by the window test :679 for row p
  * (hi[p] >= p; hi[p] == p means no partner); dpass/drev[L] = integer cut-offs for a longer read
  * of length L (see thresholds.py): pass iff d <= dpass[L]; retry on compl_reverse iff d >= drev[L].
  * (rank, world) shards the rows cyclically (row p of the sorted batch belongs to rank p % world); a single GPU is (0, 1). */
