@@ -133,21 +133,8 @@ class ShardedEngine:
                              "dpass": np.asarray(dpass, np.uint32), "drev": np.asarray(drev, np.uint32)}, self.dev)
         return _run_shard(self.engine, job, self.dev, dist.get_rank(), dist.get_world_size())
 
-    # the consumers of the tempfile (SSG, best-hit filter, grouping) are a few milliseconds of work on one GPU:
-    # they do not shard ("replicas only"), rank 0 runs them on its own engine
-    def lines_upload(self, a, b, milli):
-        self._lines_token = None
-        return self.engine.lines_upload(a, b, milli)
-
-    def lines_hist(self):
-        return self.engine.lines_hist()
-
-    def lines_besthit(self, min_milli=0, member_bits=None):
-        return self.engine.lines_besthit(min_milli, member_bits)
-
-    def components(self, a, b, n_nodes):
-        return self.engine.components(a, b, n_nodes)
-
+    # Only the all-pairs stage shards.  The other stages (reads x consensuses, consensus x consensus, the consumers of the
+    # tempfile) are milliseconds of work: the launcher runs them on `self.engine`, rank 0's own engine ("replicas only").
     def close(self):
         broadcast_job({"op": "stop"}, self.dev)
         self.engine.close()

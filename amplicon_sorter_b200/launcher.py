@@ -63,12 +63,14 @@ def install_gpu_stage(ns, device: int = 0, stats: dict | None = None, engine_fac
     keep: dict = {}  # one engine for all the small stages of a run
 
     def small_stage_engine():
+        """Engine for the stages that do not shard (a few milliseconds of work each: reads x consensuses, consensus x
+        consensus, the consumers of the tempfile): under torchrun that is rank 0's own engine, not the sharded facade."""
         eng = engine_factory() if engine_factory else keep.get("engine")
         if eng is None:
             from .engine import Engine
 
             eng = keep["engine"] = Engine(device)
-        return eng
+        return getattr(eng, "engine", eng)  # dist.ShardedEngine.engine = the local engine
 
     # "next" row of the scope table: reads x group consensuses (:1627-1715).  One engine is kept for the
     # ~30 calls per gene group; opt out with ASB200_STAGES=process_list.

@@ -183,3 +183,27 @@ def test_rewritten_reference_functions_reproduce_the_golden_vectors(path, tmp_pa
             ns["read_indexes"](gname)
         del ns["print"]
         assert seen["templist"] == case["templist"]
+
+
+def test_small_stages_use_the_local_engine_under_torchrun(tmp_path):
+    """dist.ShardedEngine only shards compare_batch; every other stage must get rank 0's own engine."""
+    script = tmp_path / "stub.py"
+    script.write_text("def process_list(self, tempfile):\n    pass\n\ndef process_consensuslist(indexes, grouplist, group_filename):\n    pass\n\n"
+                      "def do_parallel(*a):\n    pass\n\ndef SSG(tempfile):\n    pass\n\nif __name__ == '__main__':\n    pass\n")
+    ns, _ = launcher.load_reference(str(script))
+    local = OracleEngine()
+    facade = types.SimpleNamespace(engine=local, compare_batch=None)  # what dist.ShardedEngine looks like
+    seen = []
+    import amplicon_sorter_b200.host as host_mod
+    real = host_mod.iden_consensus_files
+    host_mod.iden_consensus_files = lambda outputfolder, consensus_tempfile, stringx, engine: seen.append(engine)
+    try:
+        launcher.install_gpu_stage(ns, engine_factory=lambda: facade)
+
+        def iden_consensus():
+            pass
+
+        ns["do_parallel"]("out", 1, "c.tmp", iden_consensus, "x", "g")
+    finally:
+        host_mod.iden_consensus_files = real
+    assert seen == [local]
