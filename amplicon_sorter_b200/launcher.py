@@ -238,6 +238,14 @@ def main(argv=None):
         del argv[k:k + 2]
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         return main_distributed(find_script(script), argv)
+    # Fail loudly BEFORE the reference runs: its per-file `except Exception: continue` (:2184) would turn a missing GPU or
+    # a missing libasb200.so into a silently skipped input file.  There is no CPU fallback.
+    from .engine import Engine
+
+    try:
+        Engine(device).close()
+    except Exception as exc:
+        raise SystemExit(f"amplicon_sorter_b200: cannot start the CUDA engine on device {device}: {exc}")
     ns, main_code = load_reference(find_script(script))
     install_gpu_stage(ns, device)
     execute(ns, main_code, argv)

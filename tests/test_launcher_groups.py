@@ -207,3 +207,20 @@ def test_small_stages_use_the_local_engine_under_torchrun(tmp_path):
     finally:
         host_mod.iden_consensus_files = real
     assert seen == [local]
+
+
+def test_launcher_fails_loudly_without_an_engine(tmp_path, monkeypatch):
+    """No CPU fallback: the launcher must stop before the reference's `except Exception: continue` can hide the failure."""
+    import amplicon_sorter_b200.engine as engine_mod
+    from amplicon_sorter_b200._ffi import EngineError
+
+    def boom(*a, **k):
+        raise EngineError(-1, "asb_create failed (no usable CUDA device?)")
+
+    monkeypatch.setattr(engine_mod, "Engine", boom)
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    script = tmp_path / "stub.py"
+    script.write_text("def process_list(self, tempfile):\n    pass\n\nif __name__ == '__main__':\n    raise AssertionError('the script must not start')\n")
+    with pytest.raises(SystemExit) as e:
+        launcher.main(["--script", str(script), "-i", "x.fastq"])
+    assert "cannot start the CUDA engine" in str(e.value)
