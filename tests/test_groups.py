@@ -156,3 +156,53 @@ def test_degenerate_line_sets(engine):
     assert label.tolist() == [0, 1, 2, 3, 4]
     with pytest.raises(Exception):
         engine.lines_upload(np.array([1], np.uint32), np.array([2], np.uint32), np.array([1001], np.uint32))
+
+
+def test_process_list_leaves_the_lines_of_the_file_it_wrote(tmp_path):
+    """host.process_list hands the integer lines to the consumers (groups.CACHE): they must be the file's lines."""
+    import types
+
+    from amplicon_sorter_b200 import host
+    from tests.test_golden import load as load_g, rebuild_comparelist2
+
+    fx = load_g(os.path.join(HERE, "golden", "g2_random.json.gz"))  # -ra mode: several overlapping batches, one engine batch
+    args = types.SimpleNamespace(outputfolder=str(tmp_path), similar_genes=fx["similar_genes"], nprocesses=1)
+    open(os.path.join(str(tmp_path), "results.txt"), "w").close()
+    path = os.path.join(str(tmp_path), "x_compare.tmp")
+    host.process_list(rebuild_comparelist2(fx), path, args, engine=OracleEngine())
+    cached = groups.lines_for(path)
+    parsed = groups.Lines.from_text(open(path).read())
+    assert open(path).read() == fx["compare_tmp"] and len(cached) == len(parsed) > 0
+    for f in ("a", "b", "milli", "rev"):
+        assert np.array_equal(getattr(cached, f), getattr(parsed, f)), f
+    # a file that changed on disk is re-parsed, a missing one raises like the reference's open()
+    with open(path, "a") as f:
+        f.write("1:2:0.9\n")
+    assert len(groups.lines_for(path)) == len(parsed) + 1
+    os.remove(path)
+    with pytest.raises(FileNotFoundError):
+        groups.lines_for(path)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomised_host_logic_against_the_statement_by_statement_restatement(seed):
+    """Small random files with heavy ties, repeated pairs and both admission modes."""
+    rnd = random.Random(100 + seed)
+    n_idx = rnd.choice([5, 12, 40])
+    n = rnd.choice([1, 30, 400, 2000])
+    rows = []
+    for _ in range(n):
+        a, b = rnd.sample(range(n_idx), 2)
+        rows.append(f"{a}:{b}:{groups.IDEN_STR[rnd.choice([1000, 990, 985, 950, 900, rnd.randrange(500, 1001)])]}" + (":reverse" if rnd.random() < 0.3 else ""))
+    text = "\n".join(rows) + "\n"
+    lines = groups.Lines.from_text(text)
+    eng = OracleEngine()
+    assert groups.ssg_estimate(eng, lines) == oracle.py_ssg(text)
+    members = set(str(v) for v in rnd.sample(range(n_idx), max(1, n_idx // 2)))
+    for ssg, idx, as_list in ((None, None, False), (0.95, members, True), (0.5, members, True), (1.01, members, True)):
+        want = oracle.py_besthit_templist(text, ssg, idx)
+        got, *_ = groups.best_hits(eng, lines, ssg, idx)
+        assert got == want
+        n_greedy, merged = groups.make_groups(eng, got, update_with_list=as_list)
+        w_greedy, w_merged = oracle.py_groups(want, update_with_list=as_list)
+        assert n_greedy == w_greedy and [list(g) for g in merged] == [list(g) for g in w_merged]
