@@ -19,6 +19,7 @@ class Engine:
         self._h = h
         self.device = device
         self.n_reads = 0
+        self._lines_token = None  # groups.upload: the Lines object whose arrays are resident on the device
 
     # -- plumbing ------------------------------------------------------------------------------
     def _check(self, rc):

@@ -15,6 +15,8 @@ stable sorts, the leftovers of lower scores in the per-key lists) is reproduced,
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 IDEN_STR = [str(m / 1000) for m in range(1001)]  # the text of iden = m/1000 as the reference writes it
@@ -67,8 +69,6 @@ CACHE: dict = {}
 def lines_for(path: str) -> Lines:
     """The integer lines of the tempfile at `path`: from the stage that wrote it, else parsed from the text.
     Raises FileNotFoundError like the reference's open() when the file does not exist (:1014, :1392)."""
-    import os
-
     key = os.path.abspath(path)
     if not os.path.exists(path):
         CACHE.pop(key, None)

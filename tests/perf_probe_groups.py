@@ -9,7 +9,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, ".")
-from amplicon_sorter_b200 import groups, synth, thresholds  # noqa: E402
+from amplicon_sorter_b200 import groups, synth  # noqa: E402
 from amplicon_sorter_b200.engine import Engine  # noqa: E402
 from oracle import oracle  # noqa: E402
 from tests import util  # noqa: E402

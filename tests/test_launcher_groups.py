@@ -13,8 +13,7 @@ import types
 
 import pytest
 
-from amplicon_sorter_b200 import groups, launcher
-from oracle import oracle
+from amplicon_sorter_b200 import launcher
 from tests.fake_engine import OracleEngine
 
 HERE = os.path.dirname(os.path.abspath(__file__))
