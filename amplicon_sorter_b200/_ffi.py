@@ -11,13 +11,15 @@ from . import build as _build
 RECORD = np.dtype([("i_pos", "<u4"), ("j_pos", "<u4"), ("d", "<u4"), ("reverse", "<u4")])
 
 ASB_OK, ASB_DONE = 0, 1
+TEXT_MAX_LINE = 40  # >= kTextMaxLine of csrc/text.cuh: bytes of the longest possible line
 
 
 class StepInfo(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("n_records", C.c_uint64), ("fwd_survivors", C.c_uint64),
                 ("rc_survivors", C.c_uint64), ("zone_checks", C.c_uint64), ("word_updates", C.c_uint64),
                 ("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("screen_ms", C.c_float), ("total_ms", C.c_float),
-                ("launches", C.c_uint32), ("reserved", C.c_uint32), ("screen_word_updates", C.c_uint64)]
+                ("launches", C.c_uint32), ("reserved", C.c_uint32), ("screen_word_updates", C.c_uint64),
+                ("useful_word_updates", C.c_uint64), ("screen_useful_word_updates", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -34,7 +36,8 @@ _LIB = None
 SYMBOLS = ["asb_version", "asb_create", "asb_destroy", "asb_last_error", "asb_set_param", "asb_upload_reads",
            "asb_batch_begin", "asb_batch_step", "asb_batch_records", "asb_distance_pairs", "asb_debug_read", "asb_batch_records_dev", "asb_int_peak", "asb_format_records",
            "asb_kmer_build", "asb_kmer_shared_pairs", "asb_kmer_shared_tile", "asb_threeway_pairs",
-           "asb_lines_upload", "asb_lines_hist", "asb_lines_besthit", "asb_lines_besthit_fetch", "asb_components"]
+           "asb_lines_upload", "asb_lines_hist", "asb_lines_besthit", "asb_lines_besthit_fetch", "asb_components",
+           "asb_text_begin", "asb_text_step", "asb_host_alloc", "asb_host_free", "asb_lines_count", "asb_lines_fetch"]
 
 
 def lib_path() -> str:
@@ -79,6 +82,15 @@ def load():
     L.asb_lines_besthit.argtypes = [vp, C.c_uint32, u32p, C.c_uint32, u64p, fp]
     L.asb_lines_besthit_fetch.argtypes = [vp, u32p, u32p]
     L.asb_components.argtypes = [vp, u32p, u32p, C.c_uint64, C.c_uint32, u32p, fp]
+    u16p = C.POINTER(C.c_uint16)
+    L.asb_text_begin.argtypes = [vp, u32p, C.c_uint32, u32p, C.c_uint32, u32p, u16p, C.c_uint32, C.c_char_p, C.c_uint32]
+    L.asb_text_step.argtypes = [vp, vp, C.c_uint64, C.c_int, vp, C.c_uint64, u64p]
+    L.asb_host_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
+    L.asb_host_free.argtypes = [vp]
+    L.asb_host_free.restype = None
+    L.asb_lines_count.argtypes = [vp]
+    L.asb_lines_count.restype = C.c_uint64
+    L.asb_lines_fetch.argtypes = [vp, u32p, u32p, u32p, u8p]
     _LIB = L
     return L
 

@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "asb200.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "myers_band.cuh"), os.path.join(_HERE, "csrc", "lines.cuh"), os.path.join(os.path.dirname(_HERE), "include", "asb200.h")]
+DEPS = [SRC, os.path.join(_HERE, "csrc", "myers_band.cuh"), os.path.join(_HERE, "csrc", "lines.cuh"), os.path.join(_HERE, "csrc", "text.cuh"), os.path.join(os.path.dirname(_HERE), "include", "asb200.h")]
 LIB = os.path.join(_HERE, "_lib", "libasb200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",

@@ -35,7 +35,7 @@ namespace asb {
 // --------------------------------------------------------------------------------------------
 // device-side views
 // --------------------------------------------------------------------------------------------
-enum Counter : int { C_TASK = 0, C_F, C_R, C_Z, C_O, C_WORDS, C_ERR, C_COUNT };
+enum Counter : int { C_TASK = 0, C_F, C_R, C_Z, C_O, C_WORDS, C_ERR, C_USEFUL, C_COUNT };
 enum Mode : int { M_SCREEN = 0, M_FWD = 1, M_RC = 2, M_ZONE = 3, M_EXACT = 4 };
 enum DevErr : unsigned long long { E_BAND = 1ull, E_TABLE = 2ull, E_LIST = 4ull };
 
@@ -72,6 +72,13 @@ struct DevBatch {
     // shared memory per warp: [peq_words match masks][kSeedBitsPad query bitset][seed_J * 16 words of profiles]
     int peq_words, warp_words;
 };
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
 
 __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
 
@@ -129,7 +136,7 @@ struct LaneJob {
 // All lanes with valid==true share query `row`.  Runs the mode's passes and routes the results.
 template <int BT>
 __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, const int mode, const uint32_t row,
-                                              const LaneJob job, unsigned long long& cols_acc)
+                                              const LaneJob job, unsigned long long& cols_acc, unsigned& useful_acc)
 {
     const int m = (int)B.pos_len[row];
     const uint8_t* q = B.codes_f + B.pos_off[row];
@@ -228,7 +235,7 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         const uint8_t* t = (phase == 1 || (mode == M_EXACT && job.strand)) ? tr : tf;
         int st, sc;
         if (use_seeds) sl.J = seed_profile(qb, (t == tr) ? sr : sf, ok ? nch : 0, hs_lane, B.seed_J);
-        band_pass<BT>(peq, B.Wpad, W, m, t, n, k, ok, g, push, sl, st, sc, cols_acc);
+        band_pass<BT>(peq, B.Wpad, W, m, t, n, k, ok, g, push, sl, st, sc, cols_acc, useful_acc);
         const bool pass = ok && st == PASS_DONE && sc <= k;
         const bool surv = ok && st == PASS_SURVIVOR;
         if (phase == 0) {
@@ -265,6 +272,7 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? 4 : 1) asb_screen(c
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* peq = smem + wid * B.warp_words;
     unsigned long long cols_acc = 0;
+    unsigned useful_acc = 0;
     for (;;) {
         unsigned long long t = 0;
         if (lane == 0) t = atomicAdd(&B.ctr[C_TASK], 1ull);
@@ -283,9 +291,11 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? 4 : 1) asb_screen(c
         job.j = row + 1 + gi * 32 + lane;
         job.valid = job.j <= B.hi[row];
         job.zval = 0; job.entry = 0; job.strand = 0;
-        process_group<BT>(B, peq, M_SCREEN, row, job, cols_acc);
+        process_group<BT>(B, peq, M_SCREEN, row, job, cols_acc, useful_acc);
     }
     if (lane == 0 && cols_acc) atomicAdd(&B.ctr[C_WORDS], cols_acc);
+    const unsigned long long useful_warp = warp_sum_u64(useful_acc);
+    if (lane == 0 && useful_warp) atomicAdd(&B.ctr[C_USEFUL], useful_warp);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -299,6 +309,7 @@ __global__ void __launch_bounds__(256) asb_lists(const DevBatch B, const int mod
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* peq = smem + wid * B.warp_words;
     unsigned long long cols_acc = 0;
+    unsigned useful_acc = 0;
     const unsigned long long n_slices = (B.list_n + 31) >> 5;
     for (;;) {
         unsigned long long t = 0;
@@ -320,11 +331,13 @@ __global__ void __launch_bounds__(256) asb_lists(const DevBatch B, const int mod
             job.zval = (mode == M_ZONE && have) ? B.list_val[e] : 0u;
             job.entry = e;
             job.strand = (mode == M_EXACT && have) ? (int)B.ex_strand[e] : 0;
-            process_group<BT>(B, peq, mode, row, job, cols_acc);
+            process_group<BT>(B, peq, mode, row, job, cols_acc, useful_acc);
             pending = pending && !job.valid;
         }
     }
     if (lane == 0 && cols_acc) atomicAdd(&B.ctr[C_WORDS], cols_acc);
+    const unsigned long long useful_warp = warp_sum_u64(useful_acc);
+    if (lane == 0 && useful_warp) atomicAdd(&B.ctr[C_USEFUL], useful_warp);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -571,6 +584,10 @@ int class_for(int need)
 
 template <typename T> struct DevBuf {
     T* p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }  // asb_destroy selects the device before the context (and its buffers) goes away
     cudaError_t ensure(size_t want) {
         if (want <= n) return cudaSuccess;
         if (p) cudaFree(p);
@@ -628,6 +645,11 @@ struct asb_ctx {
     DevBuf<uint32_t> d_la, d_lb, d_lm, d_bh_pos, d_bh_key, d_bh_alt, d_bh_alt2, d_bh_line, d_bh_first;
     uint64_t n_lines = 0, bh_n = 0; uint32_t lines_max_idx = 0;
     DevBuf<uint32_t> d_s_u32[7]; DevBuf<int32_t> d_s_i32[2]; DevBuf<uint8_t> d_s_flag; DevBuf<unsigned long long> d_s_hist;  // scratch of lines.cuh
+    // text.cuh: iden string tables of the current batch, scratch of the formatting pass, reverse flags of the resident lines
+    DevBuf<uint32_t> d_t_idx, d_t_lbase, d_t_soff, d_t_vals, d_t_vals_alt, d_t_len; DevBuf<uint16_t> d_t_milli; DevBuf<uint8_t> d_t_sbuf, d_t_text, d_lr;
+    DevBuf<uint64_t> d_t_keys, d_t_keys_alt, d_t_off;
+    uint32_t t_n_pos = 0, t_lbase_len = 0, t_n_strings = 0;
+    bool text_ready = false, lines_have_rev = false;
 };
 
 namespace {
@@ -870,6 +892,7 @@ int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, u
     if (!ctx || !offs || (!ascii && n_reads && offs[n_reads])) return fail(ctx, ASB_E_ARG, "null argument");
     CU(cudaSetDevice(ctx->device));
     ctx->in_batch = false;
+    ctx->text_ready = false;
     const uint64_t nbytes = n_reads ? offs[n_reads] : 0;
     ctx->n_reads = n_reads;
     ctx->h_roff.assign((size_t)n_reads + 1, 0);
@@ -946,6 +969,7 @@ int asb_batch_begin(asb_ctx* ctx, const uint32_t* order, uint32_t n, const uint3
     if (!ctx || (n && (!order || !hi)) || !dpass || !drev || world == 0 || rank >= world) return fail(ctx, ASB_E_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     ctx->in_batch = false;
+    ctx->text_ready = false;
     ctx->n = n; ctx->rank = rank; ctx->world = world; ctx->table_len = table_len;
     ctx->h_len.resize(n); ctx->h_hi.assign(hi, hi + n);
     std::vector<uint64_t> pos_off(n);
@@ -1030,6 +1054,7 @@ static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, 
     ctx->rec_n = nO;
     info->n_records = nO;
     info->word_updates = ctx->h_ctr[C_WORDS] * 32ull;
+    info->useful_word_updates = ctx->h_ctr[C_USEFUL] * 32ull;
     return ASB_OK;
 }
 
@@ -1115,6 +1140,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     rc = read_counters(ctx);
     if (rc) return rc;
     info->screen_word_updates = ctx->h_ctr[C_WORDS] * 32ull;
+    info->screen_useful_word_updates = ctx->h_ctr[C_USEFUL] * 32ull;
     rc = finish_lists(ctx, B, cls, zcls, (int)wmax, ctx->h_ctr[C_F], info);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -1395,3 +1421,4 @@ int asb_distance_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const
 }  // extern "C"
 
 #include "lines.cuh"
+#include "text.cuh"

@@ -187,7 +187,7 @@ int asb_lines_upload(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const u
         CU(cudaMemcpyAsync(ctx->d_lm.p, milli, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
-    ctx->n_lines = n; ctx->lines_max_idx = max_idx;
+    ctx->n_lines = n; ctx->lines_max_idx = max_idx; ctx->lines_have_rev = false;
     return ASB_OK;
 }
 

@@ -187,7 +187,10 @@ __device__ __forceinline__ void cols32_dispatch(const int len, uint32_t (&Pv)[NB
 //            lanes, while >= ~14 undecided lanes are cheaper to finish in place than to redo in lists
 //   sl     : seed lower bound of this lane's target strand (sl.J == 0: not in use), see SeedLB
 // Returns status (per lane) and, for PASS_DONE, the score D'[m][n].
-// work accumulates columns x active words executed per lane (warp-uniform) for the work counters.
+// work accumulates columns x active words executed per lane (warp-uniform) for the work counters; useful accumulates,
+// PER LANE, 32-column blocks x the words this lane itself still needed (0 for idle, dead and finished lanes): executed
+// lane-slots are 32 x work, useful ones 32 x the sum of `useful` over the lanes -- the difference is what sharing one
+// code path costs.
 //
 // Active range.  The registers Pv[0..len) / Mv[0..len) hold the words base .. base+len-1; nothing
 // else is computed.  `len` is warp-uniform (one code path), `base` is per lane: each lane keeps its
@@ -216,7 +219,7 @@ template <int BT>
 __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, const int Wpad, const int W, const int m,
                                        const uint8_t* __restrict__ tgt, const int n, const int k, const bool on,
                                        const BandGeom g, const int push_thresh, const SeedLB sl, int& status, int& score,
-                                       unsigned long long& work)
+                                       unsigned long long& work, unsigned& useful)
 {
     constexpr int NB = BT > 0 ? BT : kMaxDynWords;
     constexpr int STEP = len_step(BT);
@@ -239,6 +242,7 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
         if (__ballot_sync(0xFFFFFFFFu, alive) == 0u) { status = PASS_DEAD; score = 0; return; }
     }
     int len = min(min(Bmax, g.T0 + 1), wm + 1);  // words computed per column -- warp-uniform (shared code path)
+    if (alive) useful += (unsigned)min(min(len, ((31 + El) >> 5) + 1), wm + 1);  // words THIS lane needs in the first block
     if (BT > 0) len = min(BT, BT - ((BT - len) / STEP) * STEP);
 #pragma unroll
     for (int t = 0; t < Bmax; ++t) { Pv[t] = 0xFFFFFFFFu; Mv[t] = 0u; }
@@ -331,10 +335,12 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
             alive = need > 0;  // nothing live inside the band: this lane is > k
             if (!alive) { ntop = base; need = 0; }
         }
+
         const unsigned am = __ballot_sync(0xFFFFFFFFu, alive);
         if (am == 0u) break;
         if (__popc(am) <= push_thresh) break;
         if (c >= g.tcut && __popc(am) <= g.cont) break;
+        useful += (unsigned)need;  // the next block runs: this lane's own share of it
         int nlen = __reduce_max_sync(0xFFFFFFFFu, need);
         if (BT > 0) nlen = min(BT, BT - ((BT - nlen) / STEP) * STEP);  // round up to a compiled variant
         nlen = min(nlen, Bmax);

@@ -16,6 +16,7 @@ import os
 import numpy as np
 
 from ._ffi import RECORD
+from .engine import EngineBase
 
 
 def world():
@@ -88,39 +89,99 @@ def broadcast_job(job: dict | None, dev):
     return out
 
 
-def gather_records(recs: np.ndarray, dev):
-    """Per-rank record arrays -> merged array in (i_pos, j_pos) order on rank 0 (None elsewhere)."""
+class DistributedAbort(SystemExit):
+    """Some rank failed inside a sharded call.  A SystemExit on purpose: the reference's per-file
+    `except Exception: continue` (amplicon_sorter.py:2184) must not swallow it and walk into the next
+    collective while the other ranks are gone."""
+
+
+def agree(ok: bool, dev, what: str = ""):
+    """Collective: every rank reports whether its last engine call worked; if any did not, ALL ranks leave."""
+    import torch
+    import torch.distributed as dist
+
+    flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()):
+        raise DistributedAbort(f"amplicon_sorter_b200: rank {dist.get_rank()}: a rank failed in {what or 'a sharded call'}; aborting all ranks")
+
+
+def gather_step(mine, status: int, done: bool, dev):
+    """Per-slab K6: the ranks' record tensors ((k, 4) int32 on `dev`, each sorted) -> their concatenation on rank 0
+    (None elsewhere), all on the device: counts all_gather, padded gather over NCCL / NVLink, no host round trip.
+    The counts message also carries every rank's status and done flag, so that a failed rank (or ranks that disagree
+    on the number of slabs) stops ALL ranks at the same step instead of leaving them parked in a collective."""
     import torch
     import torch.distributed as dist
 
     w, r = dist.get_world_size(), dist.get_rank()
-    cnt = torch.tensor([recs.shape[0]], dtype=torch.int64, device=dev)
-    cnts = [torch.zeros_like(cnt) for _ in range(w)]
-    dist.all_gather(cnts, cnt)
-    sizes = [int(c.item()) for c in cnts]
-    mx = max(max(sizes), 1)
-    pad = torch.zeros((mx, 4), dtype=torch.int32, device=dev)
-    if recs.shape[0]:
-        pad[: recs.shape[0]] = torch.from_numpy(recs.view(np.uint32).reshape(-1, 4).view(np.int32)).to(dev)
-    parts = [torch.empty_like(pad) for _ in range(w)] if r == 0 else None
-    dist.gather(pad, parts, dst=0)
+    n = int(mine.shape[0]) if mine is not None else 0
+    head = torch.tensor([n, int(status), int(bool(done))], dtype=torch.int64, device=dev)
+    heads = torch.empty((w, 3), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(heads, head) if dev.type == "cuda" else dist.all_gather(list(heads.unbind(0)), head)
+    heads = heads.tolist()
+    if any(h[1] for h in heads):
+        bad = [i for i, h in enumerate(heads) if h[1]]
+        raise DistributedAbort(f"amplicon_sorter_b200: rank {r}: engine failure on rank(s) {bad}; aborting all ranks")
+    dones = {h[2] for h in heads}
+    if len(dones) != 1:
+        raise DistributedAbort(f"amplicon_sorter_b200: rank {r}: ranks disagree on the number of slabs; aborting all ranks")
+    if dones.pop():
+        return None, True
+    sizes = [h[0] for h in heads]
+    mx = max(sizes)
+    if mx == 0:
+        return (mine[:0] if r == 0 else None), False
+    pad = torch.empty((mx, 4), dtype=torch.int32, device=dev)
+    pad[:n] = mine
+    buf = torch.empty((w, mx, 4), dtype=torch.int32, device=dev) if r == 0 else None
+    dist.gather(pad, list(buf.unbind(0)) if r == 0 else None, dst=0)
     if r != 0:
+        return None, False
+    return torch.cat([buf[i, :s] for i, s in enumerate(sizes)]), False
+
+
+def gather_records(recs: np.ndarray, dev, status: int = 0):
+    """Per-rank record arrays -> merged array in (i_pos, j_pos) order on rank 0 (None elsewhere)."""
+    import torch
+
+    mine = torch.from_numpy(np.ascontiguousarray(recs).view(np.uint32).reshape(-1, 4).view(np.int32).copy()).to(dev)
+    allr, _ = gather_step(mine, status, False, dev)
+    if allr is None:
         return None
-    allr = torch.cat([p[:s] for p, s in zip(parts, sizes)])
     key = (allr[:, 0].to(torch.int64) << 32) | (allr[:, 1].to(torch.int64) & 0xFFFFFFFF)
     allr = allr[torch.argsort(key, stable=True)]
     return allr.cpu().numpy().view(np.uint32).reshape(-1).view(RECORD)
 
 
-class ShardedEngine:
-    """Engine facade for rank 0: every compare_batch is executed by all ranks on their shard."""
+class ShardedEngine(EngineBase):
+    """Engine facade for rank 0: every all-pairs call is executed by all ranks on their shard of the rows."""
 
     def __init__(self, engine, dev):
         self.engine, self.dev = engine, dev
+        self.aborted = False
+
+    def _guard(self, fn, what):
+        """Run this rank's part of a sharded call, then agree with the other ranks that it worked."""
+        err = None
+        try:
+            out = fn()
+        except Exception as exc:  # noqa: BLE001 -- reported through the collective below
+            err, out = exc, None
+        try:
+            agree(err is None, self.dev, what)
+        except DistributedAbort:
+            self.aborted = True
+            if err is not None:
+                import traceback
+
+                traceback.print_exception(err)
+            raise
+        return out
 
     def upload_reads(self, buf, offs):
         job = broadcast_job({"op": "upload", "buf": np.ascontiguousarray(buf), "offs": np.ascontiguousarray(offs)}, self.dev)
-        self.engine.upload_reads(job["buf"], job["offs"])
+        self._guard(lambda: self.engine.upload_reads(job["buf"], job["offs"]), "upload_reads")
 
     def set_param(self, name, value):
         broadcast_job({"op": "param", "name": name, "value": float(value)}, self.dev)
@@ -131,33 +192,185 @@ class ShardedEngine:
 
         job = broadcast_job({"op": "batch", "order": np.asarray(order, np.uint32), "hi": np.asarray(hi, np.uint32),
                              "dpass": np.asarray(dpass, np.uint32), "drev": np.asarray(drev, np.uint32)}, self.dev)
-        return _run_shard(self.engine, job, self.dev, dist.get_rank(), dist.get_world_size())
+        try:
+            return _run_shard(self.engine, job, self.dev, dist.get_rank(), dist.get_world_size())
+        except DistributedAbort:
+            self.aborted = True
+            raise
+
+    def compare_text(self, order, hi, dpass, drev, text_tables, sink, rank=0, world=1):
+        """Engine.compare_text over all ranks: per slab, the ranks' records are gathered on rank 0's GPU (gather_step),
+        merged, printed there (csrc/text.cuh) and handed to `sink`; the resident line set ends up on rank 0's engine."""
+        import torch.distributed as dist
+
+        job = broadcast_job({"op": "batch_text", "order": np.asarray(order, np.uint32), "hi": np.asarray(hi, np.uint32),
+                             "dpass": np.asarray(dpass, np.uint32), "drev": np.asarray(drev, np.uint32)}, self.dev)
+        try:
+            return _run_shard_text(self.engine, job, self.dev, dist.get_rank(), dist.get_world_size(), text_tables, sink)
+        except DistributedAbort:
+            self.aborted = True
+            raise
+
+    @property
+    def _lines_token(self):
+        return self.engine._lines_token
+
+    @_lines_token.setter
+    def _lines_token(self, v):
+        self.engine._lines_token = v
+
+    def lines_count(self):
+        return self.engine.lines_count()
+
+    def lines_fetch(self):
+        return self.engine.lines_fetch()
 
     # Only the all-pairs stage shards.  The other stages (reads x consensuses, consensus x consensus, the consumers of the
     # tempfile) are milliseconds of work: the launcher runs them on `self.engine`, rank 0's own engine ("replicas only").
     def close(self):
-        broadcast_job({"op": "stop"}, self.dev)
+        if not self.aborted:
+            broadcast_job({"op": "stop"}, self.dev)
         self.engine.close()
 
 
 def _run_shard(engine, job, dev, r, w):
+    """One rank's part of ShardedEngine.compare_batch (records back on the host of rank 0)."""
+    recs, tot, status = np.empty(0, dtype=RECORD), None, 0
+    try:
+        recs, tot = engine.compare_batch(job["order"], job["hi"], job["dpass"], job["drev"], r, w)
+    except Exception:  # noqa: BLE001 -- gather_step tells every rank
+        import traceback
+
+        traceback.print_exc()
+        status = 1
+    merged = gather_records(recs, dev, status)
+    tot = _sum_totals(tot, dev)
+    tot["n_records"] = int(merged.shape[0]) if merged is not None else 0
+    return merged, tot
+
+
+def _sum_totals(tot, dev):
     import torch
     import torch.distributed as dist
 
-    recs, tot = engine.compare_batch(job["order"], job["hi"], job["dpass"], job["drev"], r, w)
-    merged = gather_records(recs, dev)
     keys = sorted(k for k, v in tot.items() if isinstance(v, (int, float)))
     t = torch.tensor([float(tot[k]) for k in keys], dtype=torch.float64, device=dev)
     dist.all_reduce(t)  # sums; times become rank-sums (reported as such)
-    tot = {k: (int(v) if isinstance(tot[k], int) else float(v)) for k, v in zip(keys, t.tolist())}
-    tot["n_records"] = int(merged.shape[0]) if merged is not None else 0
-    return merged, tot
+    return {k: (int(v) if isinstance(tot[k], int) else float(v)) for k, v in zip(keys, t.tolist())}
+
+
+def _run_shard_text(engine, job, dev, r, w, text_tables, sink):
+    """One rank's part of ShardedEngine.compare_text (rank 0 prints, ranks > 0 only compare and send)."""
+    from .engine import TOTALS
+
+    tot = dict.fromkeys(TOTALS, 0)
+    tot["steps"] = 0
+    status = 0
+    try:
+        engine.batch_begin(job["order"], job["hi"], job["dpass"], job["drev"], r, w)
+        if r == 0:
+            engine.text_begin(*text_tables)
+    except Exception:  # noqa: BLE001
+        import traceback
+
+        traceback.print_exc()
+        status = 1
+    n_rec = 0
+    while True:
+        info, mine = None, None
+        if not status:
+            try:
+                info = engine.batch_step()
+                if info is not None:
+                    mine = engine.step_records_tensor(info["n_records"], dev)
+            except Exception:  # noqa: BLE001
+                import traceback
+
+                traceback.print_exc()
+                status = 1
+        merged, done = gather_step(mine, status, info is None, dev)  # raises DistributedAbort on every rank if any failed
+        if done:
+            break
+        for k in TOTALS:
+            tot[k] += info.get(k, 0)
+        tot["steps"] += 1
+        if r == 0 and merged is not None and merged.shape[0]:
+            n_rec += int(merged.shape[0])
+            try:
+                sink(engine.text_step_tensor(merged, sort=w > 1))
+            except Exception:  # noqa: BLE001 -- the next gather_step tells the other ranks
+                import traceback
+
+                traceback.print_exc()
+                status = 1
+    tot = _sum_totals(tot, dev)
+    tot["n_records"] = n_rec
+    return tot
+
+
+_REGION: dict = {}
+
+
+def _region_begin(dev):
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        dist.barrier()
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+        _REGION["ev0"] = torch.cuda.Event(enable_timing=True)
+        _REGION["ev0"].record(torch.cuda.current_stream(dev))
+    _REGION["t0"] = time.perf_counter()
+
+
+def _region_end(dev) -> float:
+    import time
+
+    import torch
+    import torch.distributed as dist
+
+    dev_s = 0.0
+    if dev.type == "cuda":
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record(torch.cuda.current_stream(dev))
+    if dist.is_initialized():
+        dist.barrier()
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+        dev_s = _REGION["ev0"].elapsed_time(ev1) / 1e3
+    t = torch.tensor([max(time.perf_counter() - _REGION["t0"], dev_s)], dtype=torch.float64, device=dev)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+class Region:
+    """A timed region over all ranks (measurement hook of the sharded path): barrier + synchronize on both sides,
+    device time from CUDA events on the shared stream, wall time beside it, MAX over ranks.  Rank 0 calls begin() /
+    end(); the workers take part from worker_loop."""
+
+    def __init__(self, facade, dev, world: int):
+        self.facade, self.dev, self.world = facade, dev, world
+
+    def begin(self):
+        if self.world > 1:
+            broadcast_job({"op": "region_begin"}, self.dev)
+        _region_begin(self.dev)
+
+    def end(self) -> float:
+        if self.world > 1:
+            broadcast_job({"op": "region_end"}, self.dev)
+        return _region_end(self.dev)
 
 
 def worker_loop(engine, dev):
     """Ranks > 0: serve rank 0's jobs until it sends 'stop'."""
     import torch.distributed as dist
 
+    facade = ShardedEngine(engine, dev)
     while True:
         job = broadcast_job(None, dev)
         op = job["op"]
@@ -165,8 +378,14 @@ def worker_loop(engine, dev):
             engine.close()
             return
         if op == "upload":
-            engine.upload_reads(job["buf"], job["offs"])
+            facade._guard(lambda: engine.upload_reads(job["buf"], job["offs"]), "upload_reads")
         elif op == "param":
             engine.set_param(job["name"], job["value"])
         elif op == "batch":
             _run_shard(engine, job, dev, dist.get_rank(), dist.get_world_size())
+        elif op == "region_begin":
+            _region_begin(dev)
+        elif op == "region_end":
+            _region_end(dev)
+        elif op == "batch_text":
+            _run_shard_text(engine, job, dev, dist.get_rank(), dist.get_world_size(), None, None)

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -9,7 +10,55 @@ from . import _ffi
 from ._ffi import RECORD, EngineError, StepInfo, ptr
 
 
-class Engine:
+class TextChunk:
+    """One slab of tempfile text: `data` is a bytes-like view that stays valid until release()."""
+
+    __slots__ = ("data", "_slot")
+
+    def __init__(self, data, slot=None):
+        self.data, self._slot = data, slot
+
+    def release(self):
+        if self._slot is not None:
+            self._slot.free.set()
+            self._slot = None
+
+
+class _Slot:
+    __slots__ = ("ptr", "cap", "free")
+
+    def __init__(self):
+        self.ptr, self.cap, self.free = None, 0, threading.Event()
+        self.free.set()
+
+
+TOTALS = ("pairs", "n_records", "fwd_survivors", "rc_survivors", "zone_checks", "word_updates", "screen_word_updates",
+          "useful_word_updates", "screen_useful_word_updates", "screen_ms", "total_ms", "launches")
+
+
+class EngineBase:
+    """What every engine offers on top of batch_begin / batch_step / text_begin / text_step."""
+
+    def compare_text(self, order, hi, dpass, drev, text_tables, sink, rank=0, world=1):
+        """All steps of one batch, the lines of every step handed to `sink(chunk)` in file order as they are produced
+        (the next slab is compared while a writer thread appends the previous one).  Returns the totals dict."""
+        self.batch_begin(order, hi, dpass, drev, rank, world)
+        self.text_begin(*text_tables)
+        tot = dict.fromkeys(TOTALS, 0)
+        tot["steps"] = 0
+        while True:
+            info = self.batch_step()
+            if info is None:
+                break
+            for k in TOTALS:
+                tot[k] += info.get(k, 0)
+            tot["steps"] += 1
+            if info["n_records"]:
+                sink(self.text_step(info["n_records"]))
+        return tot
+
+
+class Engine(EngineBase):
     def __init__(self, device: int = 0, stream: int | None = None):
         self._lib = _ffi.load()
         h = C.c_void_p()
@@ -20,6 +69,8 @@ class Engine:
         self.device = device
         self.n_reads = 0
         self._lines_token = None  # groups.upload: the Lines object whose arrays are resident on the device
+        self._slots = [_Slot() for _ in range(3)]  # pinned host buffers of the text ring
+        self._slot_next = 0
 
     # -- plumbing ------------------------------------------------------------------------------
     def _check(self, rc):
@@ -29,8 +80,20 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            self._evict_lines()
+            for sl in self._slots:
+                sl.free.wait()
+                if sl.ptr:
+                    self._lib.asb_host_free(sl.ptr)
+                    sl.ptr, sl.cap = None, 0
             self._lib.asb_destroy(self._h)
             self._h = None
+
+    def _evict_lines(self):
+        """The resident line set is about to be replaced: let its owner (groups.DeviceLines) take a host copy first."""
+        tok, self._lines_token = self._lines_token, None
+        if tok is not None and hasattr(tok, "materialize"):
+            tok.materialize()
 
     def __del__(self):
         try:
@@ -132,8 +195,65 @@ class Engine:
         a = np.ascontiguousarray(a, dtype=np.uint32)
         b = np.ascontiguousarray(b, dtype=np.uint32)
         milli = np.ascontiguousarray(milli, dtype=np.uint32)
+        self._evict_lines()
         self._check(self._lib.asb_lines_upload(self._h, ptr(a, C.c_uint32), ptr(b, C.c_uint32), ptr(milli, C.c_uint32), a.shape[0]))
-        self._lines_token = None
+
+    def lines_count(self) -> int:
+        return int(self._lib.asb_lines_count(self._h))
+
+    def lines_fetch(self):
+        """(a, b, milli, rev) of the resident line set written by text_step."""
+        n = self.lines_count()
+        a, b, m = (np.empty(n, dtype=np.uint32) for _ in range(3))
+        r = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.asb_lines_fetch(self._h, ptr(a, C.c_uint32), ptr(b, C.c_uint32), ptr(m, C.c_uint32), ptr(r, C.c_uint8)))
+        return a, b, m, r.astype(bool)
+
+    # -- the tempfile as text, assembled on the device --------------------------------------------------
+    def text_begin(self, idx_sorted, lbase, soff, milli, sbuf: bytes):
+        idx_sorted = np.ascontiguousarray(idx_sorted, dtype=np.uint32)
+        lbase = np.ascontiguousarray(lbase, dtype=np.uint32)
+        soff = np.ascontiguousarray(soff, dtype=np.uint32)
+        milli = np.ascontiguousarray(milli, dtype=np.uint16)
+        self._evict_lines()
+        self._check(self._lib.asb_text_begin(self._h, ptr(idx_sorted, C.c_uint32), idx_sorted.shape[0], ptr(lbase, C.c_uint32), lbase.shape[0],
+                                             ptr(soff, C.c_uint32), ptr(milli, C.c_uint16), milli.shape[0], sbuf, len(sbuf)))
+
+    def _acquire_slot(self, cap: int) -> _Slot:
+        sl = self._slots[self._slot_next]
+        self._slot_next = (self._slot_next + 1) % len(self._slots)
+        sl.free.wait()  # the writer thread is done with this buffer
+        if sl.cap < cap:
+            if sl.ptr:
+                self._lib.asb_host_free(sl.ptr)
+                sl.ptr, sl.cap = None, 0
+            want = max(cap + cap // 2, 1 << 20)
+            p = C.c_void_p()
+            if self._lib.asb_host_alloc(want, C.byref(p)) != 0:
+                raise EngineError(-3, f"cannot pin {want} bytes of host memory for the tempfile text")
+            sl.ptr, sl.cap = p.value, want
+        return sl
+
+    def text_step(self, n_records: int, dev_ptr: int | None = None, sort: bool = False) -> TextChunk:
+        """Lines of the last step's records (dev_ptr None) or of n_records asb_records in device memory at dev_ptr."""
+        sl = self._acquire_slot(_ffi.TEXT_MAX_LINE * int(n_records) + 64)
+        nb = C.c_uint64()
+        self._check(self._lib.asb_text_step(self._h, C.c_void_p(dev_ptr) if dev_ptr else None, int(n_records), int(bool(sort)),
+                                            C.c_void_p(sl.ptr), sl.cap, C.byref(nb)))
+        sl.free.clear()
+        return TextChunk(memoryview((C.c_char * nb.value).from_address(sl.ptr)).cast("B"), sl)
+
+    def step_records_tensor(self, n_records: int, dev):
+        """The last step's records as an (n, 4) int32 tensor on this engine's GPU (for the NCCL gather)."""
+        import torch
+
+        t = torch.empty((int(n_records), 4), dtype=torch.int32, device=dev)
+        if n_records:
+            self.batch_records_dev(t.data_ptr())
+        return t
+
+    def text_step_tensor(self, recs, sort: bool = True) -> TextChunk:
+        return self.text_step(int(recs.shape[0]), recs.data_ptr(), sort)
 
     def lines_hist(self):
         """(hist[1001] of iden*1000 over the resident lines, device ms)."""

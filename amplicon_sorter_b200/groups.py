@@ -36,6 +36,9 @@ class Lines:
     def __len__(self):
         return int(self.a.shape[0])
 
+    def discard(self):
+        """The file these lines belong to is gone: nobody will ask for them again."""
+
     @classmethod
     def from_text(cls, text: str):
         """Parse ``idxA:idxB:iden[:reverse]`` lines (used when the stage that wrote the file did not leave its arrays)."""
@@ -62,7 +65,38 @@ class Lines:
                    np.concatenate([p.milli for p in parts]), np.concatenate([p.rev for p in parts]))
 
 
-# lines left behind by host.process_list, keyed by the absolute path of the tempfile it wrote
+class DeviceLines(Lines):
+    """The line set host.process_list left RESIDENT on `engine`'s GPU (csrc/text.cuh appends the integer form of every
+    line it prints).  Host copies are taken only when somebody asks for them -- or when the engine is about to replace
+    its resident set (Engine._evict_lines)."""
+
+    def __init__(self, engine):
+        self._engine = engine
+        self._n = int(engine.lines_count())
+        self._host = None
+        engine._lines_token = self
+
+    def materialize(self):
+        if self._host is None:
+            self._host = self._engine.lines_fetch()
+            self._engine = None
+        return self._host
+
+    a = property(lambda self: self.materialize()[0])
+    b = property(lambda self: self.materialize()[1])
+    milli = property(lambda self: self.materialize()[2])
+    rev = property(lambda self: self.materialize()[3])
+
+    def __len__(self):
+        return self._n
+
+    def discard(self):
+        eng, self._engine = self._engine, None
+        if eng is not None and getattr(eng, "_lines_token", None) is self:
+            eng._lines_token = None  # no host copy needed when the engine replaces its resident set
+
+
+# lines left behind by host.process_list, keyed by the absolute path of the tempfile it wrote (one file at a time)
 CACHE: dict = {}
 
 

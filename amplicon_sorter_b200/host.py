@@ -96,6 +96,72 @@ def format_records(records: np.ndarray, idx_sorted: np.ndarray, lens_sorted: np.
     return text, (idx32[records["i_pos"]], idx32[records["j_pos"]], milli[e], records["reverse"] != 0)
 
 
+def text_tables(idx_sorted: np.ndarray, lens_sorted: np.ndarray, dpass: np.ndarray):
+    """What asb_text_begin needs to print the lines of amplicon_sorter.py:792-798 on the device: the idx printed for
+    every sorted position, and Python's own ``str(round(1 - d/L, 3))`` (:233) for every (L, d) a record can carry --
+    every length L present in the batch, d = 0 .. dpass[L] (an emitted distance never exceeds the pass cut-off of its
+    longer read).  String number lbase[L] + d; milli = iden * 1000 is the integer form the consumers of the file use."""
+    lens = np.unique(np.asarray(lens_sorted, dtype=np.int64))
+    lmax = int(lens[-1]) if lens.size else 0
+    lbase = np.full(lmax + 1, 0xFFFFFFFF, dtype=np.uint32)
+    strs, n = [], 0
+    for length in lens.tolist():
+        cap = int(dpass[length]) if length < dpass.shape[0] else 0xFFFFFFFF
+        if length <= 0 or cap == 0xFFFFFFFF:  # no distance passes for that length
+            continue
+        lbase[length] = n
+        strs.extend(round(1 - dd / length, 3) for dd in range(cap + 1))
+        n += cap + 1
+    milli = np.fromiter((int(round(v * 1000)) for v in strs), dtype=np.uint16, count=n)  # exact: v has <= 3 decimals
+    strs = [str(v) for v in strs]
+    soff = np.zeros(n + 1, dtype=np.uint32)
+    np.cumsum(np.fromiter((len(t) for t in strs), dtype=np.uint32, count=n), out=soff[1:])
+    return np.ascontiguousarray(idx_sorted, dtype=np.uint32), lbase, soff, milli, "".join(strs).encode("ascii")
+
+
+class TextSink:
+    """Appends the slabs of text to the tempfile on a writer thread, so that write(2) of one slab overlaps the GPU
+    work on the next (the reference appends per 1 M-pair chunk, amplicon_sorter.py:802-807).  Callable: sink(chunk)."""
+
+    def __init__(self, path: str):
+        import queue
+        import threading
+
+        self.f = open(path, "ab", buffering=0)  # :803 append mode
+        self.q = queue.Queue()
+        self.err = None
+        self.bytes = 0
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def __call__(self, chunk):
+        self.q.put(chunk)
+
+    def _run(self):
+        while True:
+            c = self.q.get()
+            if c is None:
+                return
+            try:
+                if self.err is None:
+                    mv = memoryview(c.data)
+                    off = 0
+                    while off < len(mv):
+                        off += self.f.write(mv[off:])
+                    self.bytes += len(mv)
+            except BaseException as exc:  # reported by close()
+                self.err = exc
+            finally:
+                c.release()
+
+    def close(self):
+        self.q.put(None)
+        self.t.join()
+        self.f.close()
+        if self.err is not None:
+            raise self.err
+
+
 class AllPairs:
     """State shared by the batches of one input file: one engine, reads uploaded once."""
 
@@ -112,34 +178,30 @@ class AllPairs:
         self.engine.upload_reads(buf, offs)
         self.lens = lens.astype(np.int64)
 
-    def compare(self, read_ids: np.ndarray, similar_genes: float, rank=0, world=1):
-        """One batch (read ids in the batch's CURRENT list order).  Returns (order, records, tl)."""
-        read_ids = np.asarray(read_ids, dtype=np.int64)
-        lens = self.lens[read_ids]
-        perm = np.argsort(lens, kind="stable")  # d.sort(key=lambda x: len(x[1]))  :669
-        order = read_ids[perm].astype(np.uint32)
-        lens_sorted = lens[perm]
-        hi = batch_geometry(lens_sorted)
-        tl = int((hi.astype(np.int64) - np.arange(hi.shape[0])).sum())
-        if tl == 0:
-            return perm, order, lens_sorted, np.empty(0, dtype=self._rec_dtype()), 0
-        max_len = int(lens_sorted[-1])
-        dpass, drev = thresholds.tables(similar_genes / 100, max_len + 1)  # similarg :783
-        recs, tot = self.engine.compare_batch(order, hi, dpass, drev, rank, world)
+    def _account(self, tot):
         self.stats["pairs"] += tot["pairs"]
         self.stats["records"] += tot["n_records"]
         for k in ("fwd_survivors", "rc_survivors", "zone_checks", "word_updates", "screen_ms"):
-            self.stats[k] += tot[k]
-        self.stats["gpu_ms"] += tot["total_ms"]
-        self.last_dpass = dpass
-        return perm, order, lens_sorted, recs, tl
+            self.stats[k] += tot.get(k, 0)
+        self.stats["gpu_ms"] += tot.get("total_ms", 0.0)
 
-    def compare_many(self, batches_read_ids, similar_genes: float, rank=0, world=1):
+    def compare(self, read_ids: np.ndarray, similar_genes: float, rank=0, world=1):
+        """One batch (read ids in the batch's CURRENT list order) -> (perm, order, lens_sorted, records, tl)."""
+        perms, order, lens_sorted, hi, tl = self.plan([read_ids])
+        if tl == 0:
+            return perms[0], order, lens_sorted, np.empty(0, dtype=self._rec_dtype()), 0
+        dpass, drev = thresholds.tables(similar_genes / 100, int(lens_sorted[-1]) + 1)  # similarg :783
+        recs, tot = self.engine.compare_batch(order, hi, dpass, drev, rank, world)
+        self._account(tot)
+        self.last_dpass = dpass
+        return perms[0], order, lens_sorted, recs, tl
+
+    def plan(self, batches_read_ids):
         """All batches of one input file as ONE engine batch: the length-sorted batches are laid end to end
         (position = batch offset + position in the batch), a row's window never leaves its own batch, and the
         records come back in (batch, i, j) order -- the order of the reference's file.  A default-mode run is
         dozens of 1,000-read batches of 0.5 M pairs each; one launch per batch cannot fill 148 SMs.
-        Returns (perms per batch, order, lens_sorted, records with GLOBAL positions, tl)."""
+        Returns (perms per batch, order, lens_sorted, hi with GLOBAL positions, tl)."""
         perms, orders, lens_all, his = [], [], [], []
         base = 0
         for read_ids in batches_read_ids:
@@ -154,18 +216,21 @@ class AllPairs:
         order = np.concatenate(orders) if orders else np.zeros(0, np.uint32)
         lens_sorted = np.concatenate(lens_all) if lens_all else np.zeros(0, np.int64)
         hi = (np.concatenate(his) if his else np.zeros(0, np.int64)).astype(np.uint32)
-        tl = int((hi.astype(np.int64) - np.arange(hi.shape[0])).sum())
-        if tl == 0:
-            return perms, order, lens_sorted, np.empty(0, dtype=self._rec_dtype()), 0
+        tl = int((hi.astype(np.int64) - np.arange(hi.shape[0])).sum())  # the reference's tl (:684)
+        return perms, order, lens_sorted, hi, tl
+
+    def compare_to_file(self, order, lens_sorted, hi, idx_sorted, similar_genes: float, out_path: str):
+        """Decide every pair of the planned batch and append the lines to `out_path` as they are produced."""
         dpass, drev = thresholds.tables(similar_genes / 100, int(lens_sorted.max()) + 1)  # similarg :783
-        recs, tot = self.engine.compare_batch(order, hi, dpass, drev, rank, world)
-        self.stats["pairs"] += tot["pairs"]
-        self.stats["records"] += tot["n_records"]
-        for k in ("fwd_survivors", "rc_survivors", "zone_checks", "word_updates", "screen_ms"):
-            self.stats[k] += tot[k]
-        self.stats["gpu_ms"] += tot["total_ms"]
-        self.last_dpass = dpass
-        return perms, order, lens_sorted, recs, tl
+        tables = text_tables(idx_sorted, lens_sorted, dpass)
+        sink = TextSink(out_path)
+        try:
+            tot = self.engine.compare_text(order, hi, dpass, drev, tables, sink)
+        finally:
+            sink.close()
+        self._account(tot)
+        self.stats["text_bytes"] = self.stats.get("text_bytes", 0) + sink.bytes
+        return tot
 
     @staticmethod
     def _rec_dtype():
@@ -173,7 +238,7 @@ class AllPairs:
         return RECORD
 
 
-def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: dict | None = None):
+def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: dict | None = None, device: int = 0):
     """Drop-in for ``process_list(self, tempfile)`` (amplicon_sorter.py:647).
 
     self     : comparelist2 -- list of batches of [id, SEQ, tag, idx] records (:568-622)
@@ -185,6 +250,9 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
     empty) whenever at least one pair was compared (:802-807 opens it in append mode per chunk);
     (3) zero comparable pairs -> 'No reads to compare, exiting...' is appended to results.txt and an
     Exception skips the file (:702-706, :768-772); (4) stale *.todo spool files are removed (:655-660).
+
+    The lines are assembled on the GPU slab by slab (csrc/text.cuh) and appended by a writer thread while the next
+    slab is compared; the same lines stay on the device in integer form for SSG / update_list / read_indexes.
     """
     outputfolder = args.outputfolder
     for x in glob.glob(os.path.join(outputfolder, "*.todo")):
@@ -213,30 +281,24 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
                 seqs.append(rec[1])
             rids[t] = rid
         batch_rids.append(rids)
-    rid_to_idx = np.empty(len(seqs), dtype=np.int64)
-    for key, rid in idx_to_rid.items():
-        rid_to_idx[rid] = key
+    rid_to_idx = np.fromiter(idx_to_rid.keys(), dtype=np.int64, count=len(seqs))  # dicts keep insertion order = rid order
 
     from . import groups
 
-    ap = AllPairs(engine)
+    ap = AllPairs(engine, device)
     ap.upload(seqs)
-    wrote = False
-    line_parts = []
     live = [(d, rids) for d, rids in zip(self, batch_rids) if len(d)]
-    perms, order, lens_sorted, recs, tl_total = ap.compare_many([rids for _, rids in live], args.similar_genes)
+    perms, order, lens_sorted, hi, tl_total = ap.plan([rids for _, rids in live])
     for (d, _), perm in zip(live, perms):
         d[:] = [d[i] for i in perm.tolist()]  # side effect (1): batch left length-sorted in place
+    for old, _ in groups.CACHE.values():  # lines of an earlier input file are never asked for again (:2179 deletes that file)
+        old.discard()
+    groups.CACHE.clear()
     if tl_total:
-        # records are sorted by (global i, global j) = (batch, i, j): the reference's -np 1 file order
-        text, ints = format_records(recs, rid_to_idx[order.astype(np.int64)], lens_sorted, getattr(ap, "last_dpass", None),
-                                    with_lines=True)
-        with open(out_path, "a") as f:  # :803
-            f.write(text)
-        wrote = True
-        line_parts.append(groups.Lines(*ints))
-    if wrote:  # the consumers of the file (SSG, update_list, read_indexes) get its lines without parsing the text
-        groups.CACHE[os.path.abspath(out_path)] = (groups.Lines.concat(line_parts), os.path.getsize(out_path))
+        # records come out sorted by (global i, global j) = (batch, i, j): the reference's -np 1 file order
+        ap.compare_to_file(order, lens_sorted, hi, rid_to_idx[order.astype(np.int64)], args.similar_genes, out_path)
+        # the consumers of the file (SSG, update_list, read_indexes) get its lines without parsing the text
+        groups.CACHE[os.path.abspath(out_path)] = (groups.DeviceLines(ap.engine), os.path.getsize(out_path))
     if stats_out is not None:
         stats_out.update(ap.stats)
         stats_out["tl"] = tl_total

@@ -47,55 +47,110 @@ def execute(ns, main_code, argv):
         sys.argv = old
 
 
-def install_gpu_stage(ns, device: int = 0, stats: dict | None = None, engine_factory=None):
-    """Rebind process_list (:647) in the reference's namespace to the GPU implementation.
+ALL_STAGES = ("process_list", "process_consensuslist", "iden_consensus", "groups")
 
-    engine_factory() -> engine lets the multi-GPU launcher hand in a dist.ShardedEngine; by default
-    every call creates (and closes) a single-GPU Engine on `device`."""
+
+def enabled_stages() -> set:
+    """ASB200_STAGES = comma-separated subset of ALL_STAGES to run on the GPU (default: all of them).  Every stage is
+    independent of the others; a stage that is not listed stays the reference's own CPU code."""
+    raw = os.environ.get("ASB200_STAGES")
+    if raw is None:
+        return set(ALL_STAGES)
+    want = {t.strip() for t in raw.split(",") if t.strip()}
+    unknown = want - set(ALL_STAGES)
+    if unknown:
+        raise SystemExit(f"ASB200_STAGES: unknown stage(s) {sorted(unknown)}; known: {', '.join(ALL_STAGES)}")
+    return want
+
+
+def loud(fn, passthrough=()):
+    """The reference skips an input file on ANY exception (`except Exception: continue`, amplicon_sorter.py:2184-2185)
+    without a word.  That is its protocol for `No reads to compare` (:702-706, :768-772) -- but a GPU stage has failure
+    modes the CPU path does not have (no device, out of memory, a read too long for the band, a lost rank), and those
+    must not turn into silently missing output files and exit code 0.  Anything but `passthrough` raised by a replaced
+    stage is therefore printed and turned into SystemExit, which the reference's handler does not catch."""
+    import functools
+    import traceback
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        try:
+            return fn(*a, **k)
+        except passthrough:
+            raise
+        except Exception:  # noqa: BLE001
+            traceback.print_exc()
+            raise SystemExit(f"amplicon_sorter_b200: stage {fn.__name__} failed (see the traceback above); "
+                             "stopping instead of skipping the input file silently")
+
+    return wrapper
+
+
+def install_gpu_stage(ns, device: int = 0, stats: dict | None = None, engine_factory=None, stages: set | None = None):
+    """Rebind process_list (:647) -- and the "next" stages -- in the reference's namespace to the GPU implementations.
+
+    ONE engine serves the whole run (every input file, every stage) on `device`; engine_factory() -> engine lets the
+    multi-GPU launcher hand in a dist.ShardedEngine instead.  The later CPU stages of the reference fork worker
+    processes (`Process(target=make_consensus)`, :1189-1198) while this engine's CUDA context is alive: the children
+    never touch the library (they only run the reference's own functions), which is the supported way to fork after
+    CUDA; they must be FORKED though -- the reference's functions live in a namespace that cannot be pickled for
+    spawn/forkserver -- so the start method is pinned to 'fork' here, as the reference itself does with -mac (:2136)."""
+    import multiprocessing
+
     from . import host
 
-    def process_list(self, tempfile):
-        eng = engine_factory() if engine_factory else None
-        return host.process_list(self, tempfile, ns["args"], engine=eng, stats_out=stats)
+    try:
+        multiprocessing.set_start_method("fork")
+    except RuntimeError:  # already set by the embedding program
+        if multiprocessing.get_start_method() != "fork":
+            print("asb200: multiprocessing start method is not 'fork'; the reference's worker processes need it", file=sys.stderr)
+    stages = enabled_stages() if stages is None else stages
+    keep: dict = {}
 
-    process_list.__doc__ = host.process_list.__doc__
-    ns["process_list"] = process_list
-    keep: dict = {}  # one engine for all the small stages of a run
-
-    def small_stage_engine():
-        """Engine for the stages that do not shard (a few milliseconds of work each: reads x consensuses, consensus x
-        consensus, the consumers of the tempfile): under torchrun that is rank 0's own engine, not the sharded facade."""
+    def the_engine():
         eng = engine_factory() if engine_factory else keep.get("engine")
         if eng is None:
             from .engine import Engine
 
             eng = keep["engine"] = Engine(device)
+        return eng
+
+    def small_stage_engine():
+        """Engine for the stages that do not shard (a few milliseconds of work each: reads x consensuses, consensus x
+        consensus, the consumers of the tempfile): under torchrun that is rank 0's own engine, not the sharded facade."""
+        eng = the_engine()
         return getattr(eng, "engine", eng)  # dist.ShardedEngine.engine = the local engine
 
-    # "next" row of the scope table: reads x group consensuses (:1627-1715).  One engine is kept for the
-    # ~30 calls per gene group; opt out with ASB200_STAGES=process_list.
-    if "process_consensuslist" in os.environ.get("ASB200_STAGES", "process_list,process_consensuslist"):
+    ns["__asb_engine__"] = the_engine
+    if "process_list" in stages:
+        def process_list(self, tempfile):
+            return host.process_list(self, tempfile, ns["args"], engine=the_engine(), stats_out=stats)
+
+        process_list.__doc__ = host.process_list.__doc__
+        ns["process_list"] = loud(process_list, passthrough=(host.NoReadsToCompare,))
+
+    # "next" row of the scope table: reads x group consensuses (:1627-1715)
+    if "process_consensuslist" in stages:
         def process_consensuslist(indexes, grouplist, group_filename):
-            eng = small_stage_engine()
             return host.process_consensuslist(indexes, grouplist, group_filename, args=ns["args"],
-                                              comparelist2=ns["comparelist2"], similar=ns["similar"], engine=eng)
+                                              comparelist2=ns["comparelist2"], similar=ns["similar"], engine=small_stage_engine())
 
         process_consensuslist.__doc__ = host.process_consensuslist.__doc__
-        ns["process_consensuslist"] = process_consensuslist
+        ns["process_consensuslist"] = loud(process_consensuslist)
 
-        # consensus x consensus (:1139-1158): intercept the worker-pool dispatch for that one worker
-        if "iden_consensus" in os.environ.get("ASB200_STAGES", "iden_consensus"):
-            original_do_parallel = ns["do_parallel"]
+    # consensus x consensus (:1139-1158): intercept the worker-pool dispatch for that one worker
+    if "iden_consensus" in stages:
+        original_do_parallel = ns["do_parallel"]
 
-            def do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename):
-                if getattr(worker, "__name__", "") != "iden_consensus":
-                    return original_do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename)
-                return host.iden_consensus_files(outputfolder, consensus_tempfile, stringx, engine=small_stage_engine())
+        def do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename):
+            if getattr(worker, "__name__", "") != "iden_consensus":
+                return original_do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename)
+            return loud(host.iden_consensus_files)(outputfolder, consensus_tempfile, stringx, engine=small_stage_engine())
 
-            ns["do_parallel"] = do_parallel
+        ns["do_parallel"] = do_parallel
     ns["check_version"] = lambda version: None  # :39-72 fetches GitHub and may sleep 10 s; not part of the path
-    # "next" rows 3-4: the consumers of the tempfile (SSG, best-hit filter, grouping); opt out with ASB200_STAGES
-    if "groups" in os.environ.get("ASB200_STAGES", "groups"):
+    # "next" rows 3-4: the consumers of the tempfile (SSG, best-hit filter, grouping)
+    if "groups" in stages:
         install_group_stage(ns, small_stage_engine, stats)
 
 
@@ -202,9 +257,9 @@ def install_group_stage(ns, engine_getter, stats: dict | None = None):
             print("--> Number of groups after merge: " + str(len(grouplist)))
         return grouplist
 
-    ns["__asb_update_list_filter__"] = update_list_filter
-    ns["__asb_read_indexes_filter__"] = read_indexes_filter
-    ns["__asb_groups__"] = make_groups
+    ns["__asb_update_list_filter__"] = loud(update_list_filter)
+    ns["__asb_read_indexes_filter__"] = loud(read_indexes_filter)
+    ns["__asb_groups__"] = loud(make_groups)
     calls = {"update_list": "templist = __asb_update_list_filter__(os.path.join(outputfolder, tempfile))",
              "read_indexes": "templist = __asb_read_indexes_filter__(os.path.join(outputfolder, tempfile), similar_species_groups, indexes)"}
     installed = []
@@ -216,7 +271,7 @@ def install_group_stage(ns, engine_getter, stats: dict | None = None):
         exec(compile(ast.Module(body=[new], type_ignores=[]), ns.get("__file__", "<reference>"), "exec"), ns)
         installed.append(name)
     if "SSG" in ns:
-        ns["SSG"] = SSG
+        ns["SSG"] = loud(SSG)
         installed.append("SSG")
     return installed
 
@@ -236,36 +291,60 @@ def main(argv=None):
         k = argv.index("--script")
         script = argv[k + 1]
         del argv[k:k + 2]
+    stages = enabled_stages()
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        return main_distributed(find_script(script), argv)
-    # Fail loudly BEFORE the reference runs: its per-file `except Exception: continue` (:2184) would turn a missing GPU or
-    # a missing libasb200.so into a silently skipped input file.  There is no CPU fallback.
+        return main_distributed(find_script(script), argv, stages)
+    # Fail loudly BEFORE the reference runs: there is no CPU fallback, and a missing GPU or a missing libasb200.so must
+    # not surface as "every input file skipped".
     from .engine import Engine
 
     try:
-        Engine(device).close()
+        engine = Engine(device)
     except Exception as exc:
         raise SystemExit(f"amplicon_sorter_b200: cannot start the CUDA engine on device {device}: {exc}")
     ns, main_code = load_reference(find_script(script))
-    install_gpu_stage(ns, device)
-    execute(ns, main_code, argv)
+    install_gpu_stage(ns, device, engine_factory=lambda: engine, stages=stages)
+    try:
+        execute(ns, main_code, argv)
+    finally:
+        engine.close()
 
 
-def main_distributed(script, argv):
+def main_distributed(script, argv, stages=None):
     """torchrun entry: rank 0 runs the reference, the other ranks serve its all-pairs calls."""
+    import torch
+
     from . import dist
     from .engine import Engine
 
     r, w, dev = dist.init_from_env()
-    engine = Engine(dev.index if dev.type == "cuda" else 0)
+    engine, err = None, None
+    try:
+        if dev.type == "cuda":
+            # engine and torch.distributed share ONE non-default stream: the NCCL gather reads what the engine wrote
+            stream = torch.cuda.Stream(dev)
+            torch.cuda.set_stream(stream)
+            engine = Engine(dev.index, stream=stream.cuda_stream)
+        else:
+            engine = Engine(0)
+    except Exception as exc:  # noqa: BLE001 -- every rank learns about it below
+        err = exc
+    try:
+        dist.agree(err is None, dev, "engine start-up")  # one bad GPU must not leave the other ranks parked in a broadcast
+    except dist.DistributedAbort:
+        if err is not None:
+            print(f"amplicon_sorter_b200: rank {r}: cannot start the CUDA engine: {err}", file=sys.stderr)
+        raise
     if r != 0:
         return dist.worker_loop(engine, dev)
     sharded = dist.ShardedEngine(engine, dev)
     try:
         ns, main_code = load_reference(script)
-        install_gpu_stage(ns, engine_factory=lambda: sharded)
+        install_gpu_stage(ns, engine_factory=lambda: sharded, stages=stages)
         execute(ns, main_code, argv)
     finally:
+        # after a DistributedAbort the workers are gone (close() then skips the 'stop' broadcast); after any other error
+        # on rank 0 they sit in worker_loop's broadcast, where 'stop' reaches them
         sharded.close()
 
 

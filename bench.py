@@ -1,29 +1,39 @@
 #!/usr/bin/env python3
 """bench.py -- read-pair comparisons/sec of the all-pairs read-similarity path (BASELINE.json metric).
 
-Workload (configs[4] of BASELINE.json, the configuration the metric is quoted on): `--all` on
-100,000 synthetic ~1 kb ONT-like amplicon reads (200 templates, 6 % error, either strand, 1 % of
-reads carrying N), i.e. 4,999,950,000 length-compatible pairs.  One STEP = the whole job: every
-pair decided exactly as amplicon_sorter.py:776-807 decides it, records gathered on rank 0.
+Default workload = configs[4] of BASELINE.json, the configuration the metric is quoted on: `--all` on 100,000
+synthetic ~1 kb ONT-like amplicon reads (200 templates, 6 % error, either strand, 1 % of reads carrying N), i.e.
+4,999,949,987 length-compatible pairs.  `--config 1..4` runs the other BASELINE configs (parity-test shapes, not the
+headline).  One STEP = the whole job: every pair decided exactly as amplicon_sorter.py:776-807 decides it and the
+lines of <stem>_compare.tmp produced in the reference's order.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]          one rank per GPU under torchrun for N > 1
-  python bench.py --impl reference ...                          the CPU arm (oracle port, all host cores)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C]     one rank per GPU under torchrun for N > 1
+  python bench.py --impl reference ...                                   the CPU arm (oracle port, all host cores)
 
-value  : pairs/s with the reads already resident in HBM (timed region = K whole jobs, barrier +
-         synchronize on both sides, max over ranks).  Strong scaling: total work is fixed as N grows.
-e2e    : pairs/s through the C-ABI with HOST buffers: asb_upload_reads (H2D of the ASCII reads and
-         offsets) + all steps + the D2H of the merged records, per step.
-roofline: the dominant kernel asb_screen is integer-ALU bound; see DESIGN.md.
+Both arms go through the PRODUCT's code: a single GPU through `Engine`, N > 1 through `dist.ShardedEngine` on rank 0
+with the other ranks in `dist.worker_loop` (job broadcast, cyclic row shards, per-slab device-side NCCL gather).
+
+value  : pairs/s with the reads already resident in HBM: `compare_text` (all slabs: screen + list kernels, sort, text
+         assembled on the device and copied to pinned host memory) with the text dropped instead of written.
+e2e    : pairs/s of `host.process_list(comparelist2, tempfile)` -- the drop-in for amplicon_sorter.py:647 -- from
+         Python lists of records to the finished <stem>_compare.tmp on disk: string join, H2D of the reads, all slabs,
+         D2H of the text, write(2).  This is the call the reference script makes.
+roofline: the dominant kernel asb_screen is integer-ALU bound; see DESIGN.md section 4.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import random
+import shutil
 import statistics
 import sys
+import tempfile as tempfile_mod
 import threading
 import time
+import types
+import zlib
 
 import numpy as np
 
@@ -36,31 +46,66 @@ _OUT = sys.stdout
 METRIC = "read-pair comparisons/sec (all-vs-all, ~1 kb reads)"
 UNIT = "pairs/s"
 ALU_OPS_PER_WORD_UPDATE = 10  # ALU-pipe instructions per Myers word-update in asb_screen's SASS (profiles/)
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 48.7e6  # dram__bytes_read+write.sum of one asb_screen launch (ncu --set full, profiles/r1_asb_screen_ncu_full_v7.txt)
+
+# CRC-32 of the <stem>_compare.tmp text of the full-size job (and its line count), recorded from a 1-GPU run whose
+# sampled rows matched the oracle (tests/test_gpu_fullsize.py); every later run -- any kernel version, any number of
+# GPUs -- must reproduce it.  None = no constant recorded for that config yet (the run prints its CRC).
+KNOWN_TEXT_CRC = {
+    5: None,
+}
+DESCR = {
+    1: "cfg1: default batch mode on 1,000 synthetic ~700 bp reads (5 templates)",
+    2: "cfg2: --all on 10,000 synthetic reads, 3 genes (1.8 / 0.7 / 1.0 kb) x 4 species",
+    3: "cfg3: -ra, 20 random batches of 1,000 from a 10,000-read 50-species mix (~700 bp)",
+    4: "cfg4: --all on 50,000 synthetic reads, 10 loci as full (~1 kb) and nested (~870 bp) amplicons",
+    5: "cfg5: --all on 100,000 synthetic ~1 kb reads (200 templates, 6% ONT-like error, both strands, 1% with N)",
+}
 
 
-def make_workload(n_reads: int):
-    """cfg5 reads + the host-side geometry of the one `--all` batch (amplicon_sorter.py:610, :669, :679)."""
-    cache = f"/tmp/asb200_cfg5_{n_reads}.npz"
+def batches_of(cfg: int, n: int):
+    """Read ids per batch, the way read_file builds comparelist2 for the config's command line
+    (amplicon_sorter.py:568-622): default = consecutive slices of 1,000 up to maxreads (10 batches, most of them empty,
+    when exactly 1,000 reads exist), -ra = random samples of 1,000 (overlapping), -a = one batch."""
+    if cfg == 1:
+        return [list(range(k, min(k + 1000, n))) for k in range(0, 10000, 1000)]
+    if cfg == 3:
+        rnd = random.Random(103)
+        return [rnd.sample(range(n), min(1000, n)) for _ in range(max(1, (2 * n) // 1000))]
+    return [list(range(n))]
+
+
+def make_workload(cfg: int, scale: float):
+    """The config's reads, its comparelist2 batches, and the engine-level geometry of the whole job."""
+    cache = f"/tmp/asb200_cfg{cfg}_{scale:g}.npz"
     if os.path.exists(cache):
         z = np.load(cache)
         buf, offs = z["buf"], z["offs"]
     else:
-        reads, _, _ = synth.make_config(5, scale=n_reads / 100000.0)
+        reads, _, _ = synth.make_config(cfg, scale=scale)
         buf, offs = synth.pack_reads(reads)
         try:
             np.savez(cache + f".{os.getpid()}.npz", buf=buf, offs=offs)
             os.replace(cache + f".{os.getpid()}.npz", cache)
         except OSError:
             pass
-    lens = (offs[1:] - offs[:-1]).astype(np.int64)
-    order = np.argsort(lens, kind="stable").astype(np.uint32)
-    lens_sorted = lens[order]
-    hi = host.batch_geometry(lens_sorted)
-    dpass, drev = thresholds.tables(0.80, int(lens.max()) + 1)
-    tl = int((hi.astype(np.int64) - np.arange(hi.shape[0])).sum())
-    return dict(buf=buf, offs=offs, order=order, lens_sorted=lens_sorted, hi=hi, dpass=dpass, drev=drev, tl=tl,
-                n_reads=int(lens.shape[0]), mean_len=float(lens.mean()))
+    n = int(offs.shape[0] - 1)
+    text = buf.tobytes().decode("ascii")
+    o = offs.astype(np.int64)
+    seqs = [text[o[i]:o[i + 1]] for i in range(n)]
+    batches = batches_of(cfg, n)
+    ap = host.AllPairs.__new__(host.AllPairs)  # geometry only: no engine
+    ap.lens = (o[1:] - o[:-1])
+    perms, order, lens_sorted, hi, tl = ap.plan([np.asarray(b, dtype=np.int64) for b in batches if len(b)])
+    dpass, drev = thresholds.tables(0.80, int(ap.lens.max()) + 1)
+    tables = host.text_tables(order, lens_sorted, dpass)  # idx == read id in the bench
+    return dict(cfg=cfg, buf=buf, offs=offs, seqs=seqs, batches=batches, order=order, lens_sorted=lens_sorted, hi=hi, dpass=dpass,
+                drev=drev, tables=tables, tl=tl, n_reads=n, mean_len=float(ap.lens.mean()))
+
+
+def comparelist2_of(w):
+    """[[id, SEQ, 'u', idx], ...] batches as read_file leaves them (amplicon_sorter.py:551-561); -ra batches share records."""
+    recs = [[f"r{i}", s, "u", i] for i, s in enumerate(w["seqs"])]
+    return [[recs[i] for i in b] for b in w["batches"]]
 
 
 def nominal_ops(w):
@@ -120,25 +165,29 @@ class ClockSampler(threading.Thread):
 
 def cpu_baseline(w, seconds=20.0, algo="edlib_like", nthreads=0):
     """The reference's CPU arithmetic (oracle/asref.c: edlib-like band-doubling Myers, three-way rule of
-    similarity()) on all host cores, on a strided sample of the job's rows sized for ~`seconds`."""
+    similarity()) on all host cores, on a 2-D strided sample of the job's pair set sized for ~`seconds`:
+    every `rs`-th row, every `cs`-th partner of it -- a few hundred rows of equal size per thread, so the
+    sample scales with the thread count (a rows-only sample of this job is a dozen rows of unequal length)."""
     from oracle import oracle
 
     n = w["n_reads"]
     cores = oracle.host_threads() if nthreads <= 0 else nthreads
-    # calibrate on a tiny strided sample, then size the real one
-    stride = max(1, n // 8)
-    t0 = time.perf_counter()
-    _, st = oracle.process_batch(w["buf"], w["offs"], w["order"], 80.0, algo=algo, rows=(0, n, stride), nthreads=nthreads)
-    dt = max(time.perf_counter() - t0, 1e-3)
+
+    def run(rs, cs):
+        t0 = time.perf_counter()
+        _, st = oracle.process_batch(w["buf"], w["offs"], w["order"], 80.0, algo=algo, rows=(rs // 2, n, rs), nthreads=nthreads, col_step=cs)
+        return st, max(time.perf_counter() - t0, 1e-3)
+
+    rs = max(1, n // (cores * 16))
+    cs = max(1, int(round(w["tl"] / (rs * 20000.0 * cores))))  # calibration: ~20 k pairs per core
+    st, dt = run(rs, cs)
     rate = st["pairs"] / dt
-    want_pairs = rate * seconds
-    stride = int(max(1, min(n // 2, round(w["tl"] / max(want_pairs, 1.0)))))
-    t0 = time.perf_counter()
-    _, st = oracle.process_batch(w["buf"], w["offs"], w["order"], 80.0, algo=algo, rows=(stride // 2, n, stride), nthreads=nthreads)
-    dt = time.perf_counter() - t0
+    cs = max(1, int(round(w["tl"] / rs / max(rate * seconds, 1.0))))
+    st, dt = run(rs, cs)
     return {"value": st["pairs"] / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"rows {stride // 2}::{stride} of the same job ({st['pairs']} pairs, {st['alignments']} alignments, {dt:.1f} s)",
+            "sample": f"rows {rs // 2}::{rs}, every {cs}-th partner of each, of the same job ({st['pairs']} pairs, {st['alignments']} alignments, {dt:.1f} s)",
             "algorithm": "oracle/asref.c edlib-like band-doubling Myers (64-bit words) + similarity() three-way rule, pthreads",
+            "us_per_alignment_per_core": dt * cores / max(st["alignments"], 1) * 1e6,
             "pairs": st["pairs"], "seconds": dt}
 
 
@@ -146,7 +195,7 @@ def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = make_workload(a.reads)
+    w = make_workload(a.config, a.scale)
     vals, secs = [], []
     per_step = max(3.0, min(30.0, a.cpu_seconds))
     for s in range(a.warmup + a.steps):
@@ -158,12 +207,64 @@ def run_reference_arm(a):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"cfg5: --all on {w['n_reads']} synthetic ~1 kb reads, 200 templates; each step a strided row sample (~{per_step:.0f} s) of the {w['tl']}-pair job",
+            "config": {"workload": f"{DESCR[a.config]}; each step a 2-D strided sample (~{per_step:.0f} s) of the {w['tl']}-pair job",
                        "reads": w["n_reads"], "pairs_full_job": w["tl"]},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "us_per_alignment_per_core")} | {"value": v},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    ref = _reference_script_record()
+    if ref:
+        line["cpu_baseline"]["reference_script"] = ref
     print(json.dumps(line), file=_OUT, flush=True)
+
+
+def _reference_script_record():
+    """Timing of the UNMODIFIED reference script (+ in-repo edlib/Bio shims) on a GPU box's host, recorded by
+    tests/perf_reference_script.py (too slow to repeat in every bench run: the script sleeps >= 8 s per file)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_reference_script.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class NullSink:
+    """Resident arm: the text of every slab is produced (device formatting + D2H into pinned memory) and dropped."""
+
+    def __init__(self):
+        self.bytes = 0
+
+    def __call__(self, chunk):
+        self.bytes += len(chunk.data)
+        chunk.release()
+
+
+def parity_check(facade, world):
+    """Before anything is timed: a small job of the same kind through host.process_list on THIS engine stack (all
+    ranks, NCCL gather, device-side text) must give the file the CPU oracle writes."""
+    from oracle import oracle
+
+    reads, _, _ = synth.make_config(5, scale=0.012)  # 1,200 reads, 200 templates, some with N: 0.72 M pairs
+    buf, offs = synth.pack_reads(reads)
+    lens = (offs[1:] - offs[:-1]).astype(np.int64)
+    order = oracle.stable_length_order(lens)
+    want_recs, st = oracle.process_batch(buf, offs, order, 80.0)
+    want = oracle.format_lines(want_recs, order, np.arange(len(reads), dtype=np.uint32), offs)
+    tmp = tempfile_mod.mkdtemp(prefix="asb200_parity_")
+    try:
+        args = types.SimpleNamespace(outputfolder=tmp, similar_genes=80.0)
+        c2 = [[[f"r{i}", s.decode(), "u", i] for i, s in enumerate(reads)]]
+        stats = {}
+        facade.set_param("pair_cap", 1 << 17)  # several slabs, so that the per-slab gather and merge are exercised
+        host.process_list(c2, "p_compare.tmp", args, engine=facade, stats_out=stats)
+        facade.set_param("pair_cap", float(1 << 26))
+        with open(os.path.join(tmp, "p_compare.tmp"), "rb") as f:
+            got = f.read()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    ok = got == want and stats["pairs"] == st["pairs"]
+    return {"parity_check": "ok" if ok else "FAILED", "parity_job": f"cfg5 x 0.012 through host.process_list on {world} rank(s): {st['pairs']} pairs, "
+            f"{len(want_recs)} lines, file {'identical to' if ok else 'DIFFERS from'} the CPU oracle's", "parity_crc": zlib.crc32(got)}
 
 
 def main():
@@ -172,11 +273,18 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=100000, help="reads in the --all batch (BASELINE config 5 = 100000)")
+    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5], help="BASELINE.json config (default 5, the headline)")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the config's read count (debugging)")
+    ap.add_argument("--reads", type=int, default=0, help="shorthand for --scale on config 5")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--pair-cap", type=float, default=0)
+    ap.add_argument("--tmpdir", default=None, help="where the e2e arm writes <stem>_compare.tmp (default: a fresh temp dir)")
     a = ap.parse_args()
+    if a.reads:
+        a.scale = a.reads / 100000.0
     # stdout carries exactly ONE line (the JSON): everything else any library prints to fd 1 -- NCCL's
     # "NCCL version ..." banner under NCCL_DEBUG=VERSION/WARN for one -- is sent to stderr
     global _OUT
@@ -187,183 +295,157 @@ def main():
         return run_reference_arm(a)
 
     import torch
-    import torch.distributed as dist
 
+    from amplicon_sorter_b200 import dist as adist
     from amplicon_sorter_b200.engine import Engine
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, dev = adist.init_from_env()
+    stream = torch.cuda.Stream(dev)  # engine and torch.distributed share one non-default stream
+    torch.cuda.set_stream(stream)
+    eng = Engine(dev.index, stream=stream.cuda_stream)
+    if rank != 0:
+        adist.worker_loop(eng, dev)  # serves rank 0's uploads, batches and timing marks until 'stop'
+        torch.distributed.destroy_process_group()
+        return
+    facade = adist.ShardedEngine(eng, dev) if world > 1 else eng
+    region = adist.Region(facade, dev, world)
 
-    w = make_workload(a.reads)
-    stream = torch.cuda.current_stream()
-    eng = Engine(local, stream=stream.cuda_stream)
-    pinned_buf = torch.from_numpy(w["buf"]).pin_memory()
-    pinned_offs = torch.from_numpy(w["offs"].view(np.int64)).pin_memory()
-    h_buf, h_offs = pinned_buf.numpy(), pinned_offs.numpy().view(np.uint64)
-
-    rec_cap = 1 << 22
-    rec_dev = torch.empty((rec_cap, 4), dtype=torch.int32, device=dev)
-    launches = [0]
-    agg = {"pairs": 0, "word_updates": 0, "screen_word_updates": 0, "screen_ms": 0.0, "total_ms": 0.0, "screen_launches": 0, "n_records": 0}
-
-    def job(collect=None):
-        """One whole job on this rank's shard; returns the merged record tensor on rank 0 (device)."""
-        nonlocal rec_dev, rec_cap
-        eng.batch_begin(w["order"], w["hi"], w["dpass"], w["drev"], rank, world)
-        n_rec = 0
-        while True:
-            info = eng.batch_step()
-            if info is None:
-                break
-            launches[0] += info["launches"] + (1 if info["n_records"] else 0)  # screen/list kernels (+ pack); cub sorts not counted
-            if collect is not None:
-                for k in ("pairs", "word_updates", "screen_word_updates", "screen_ms", "total_ms", "n_records"):
-                    collect[k] += info[k]
-                collect["screen_launches"] += 1
-            k = info["n_records"]
-            if n_rec + k > rec_cap:
-                rec_cap = max(2 * rec_cap, n_rec + k)
-                bigger = torch.empty((rec_cap, 4), dtype=torch.int32, device=dev)
-                bigger[:n_rec] = rec_dev[:n_rec]
-                rec_dev = bigger
-            if k:
-                eng.batch_records_dev(rec_dev[n_rec:].data_ptr())
-                n_rec += k
-        mine = rec_dev[:n_rec]
-        if world == 1:
-            return mine
-        # K6: per-rank lists -> rank 0 over NCCL (counts, then padded all_gather; lists are small)
-        cnt = torch.tensor([n_rec], dtype=torch.int64, device=dev)
-        cnts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        mx = int(max(int(c.item()) for c in cnts))
-        pad = torch.zeros((mx, 4), dtype=torch.int32, device=dev)
-        pad[:n_rec] = mine
-        parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-        dist.gather(pad, parts, dst=0)
-        if rank != 0:
-            return mine
-        allr = torch.cat([p[: int(c.item())] for p, c in zip(parts, cnts)])
-        key = (allr[:, 0].to(torch.int64) << 32) | allr[:, 1].to(torch.int64)
-        return allr[torch.argsort(key)]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    w = make_workload(a.config, a.scale)
+    parity = {} if a.no_parity else parity_check(facade, world)
+    if a.pair_cap:
+        facade.set_param("pair_cap", a.pair_cap)
 
     # ---- resident-input arm -------------------------------------------------------------------
     codes_bytes = 2 * int(w["buf"].nbytes)  # forward + compl_reverse symbol codes
     flush_buf = None if codes_bytes > 126 * (1 << 20) else torch.empty(192 * (1 << 20), dtype=torch.uint8, device=dev)
-    eng.upload_reads(h_buf, h_offs)
+    facade.upload_reads(w["buf"], w["offs"])
+    sink = NullSink()
+
+    def job():
+        return facade.compare_text(w["order"], w["hi"], w["dpass"], w["drev"], w["tables"], sink)
+
     for _ in range(a.warmup):
         job()
-    barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches[0] = 0
-    t0 = time.perf_counter()
-    ev0.record(stream)
+    agg = None
+    region.begin()
     for _ in range(a.steps):
         if flush_buf is not None:
-            flush_buf.zero_()  # inputs smaller than L2 (reduced --reads only): evict them between timed steps
-        out = job(agg)
-    ev1.record(stream)
-    barrier()
-    wall = time.perf_counter() - t0
+            flush_buf.zero_()  # inputs smaller than L2 (small configs): evict them between timed steps
+        tot = job()
+        agg = tot if agg is None else {k: agg[k] + tot[k] for k in agg}
+    t_res = region.end()
     clocks = sampler.stop()
-    dev_s = ev0.elapsed_time(ev1) / 1e3
-    tmax = torch.tensor([max(wall, dev_s)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    t_res = float(tmax.item())
-    n_records = int(out.shape[0]) if rank == 0 else 0
     value = w["tl"] * a.steps / t_res
-    gpu_launches = launches[0]
+    n_records = agg["n_records"] // a.steps
+    # own kernels: screen + list kernels (info.launches, summed over ranks) + per slab on rank 0 the text kernels
+    # (len, write; + unpack at N > 1) + one record pack per rank and slab at N > 1; cub sorts / scans are not counted
+    gpu_launches = int(agg["launches"] + agg["steps"] * (2 if world == 1 else 3 + world))
 
-    # ---- end-to-end arm: host buffers in, merged records out, every step ------------------------
-    e2e = None
+    # ---- end-to-end arm: the reference-facing call, Python lists in, tempfile on disk out ----------------
+    e2e, crc = None, None
     if a.e2e_steps > 0:
-        # pinned destination of the result, sized from the resident arm's record count (buffer set-up, like the pinned inputs)
-        host_pin = torch.empty((max(n_records, 1), 4), dtype=torch.int32).pin_memory() if rank == 0 else None
-        barrier()
-        t0 = time.perf_counter()
-        d2h = 0
-        parts_ms = {"upload": 0.0, "job_and_gather": 0.0, "d2h": 0.0}
-        for _ in range(a.e2e_steps):
-            ta = time.perf_counter()
-            eng.upload_reads(h_buf, h_offs)
-            tb = time.perf_counter()
-            out = job()
-            torch.cuda.synchronize()
-            tc = time.perf_counter()
-            if rank == 0:
-                if host_pin is None or host_pin.shape[0] < out.shape[0]:
-                    host_pin = torch.empty((max(out.shape[0], 1), 4), dtype=torch.int32).pin_memory()
-                host_pin[: out.shape[0]].copy_(out, non_blocking=True)  # D2H of the merged records into pinned memory
-                torch.cuda.synchronize()
-                d2h = out.numel() * 4
-            td = time.perf_counter()
-            for k, v in zip(parts_ms, (tb - ta, tc - tb, td - tc)):
-                parts_ms[k] += v * 1e3 / a.e2e_steps
-        barrier()
-        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = (h_buf.nbytes + h_offs.nbytes + w["order"].nbytes + w["hi"].nbytes + w["dpass"].nbytes + w["drev"].nbytes) * world
-        e2e = {"value": w["tl"] * a.e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "steps": a.e2e_steps, "rank0_ms_per_step": {k: round(v, 1) for k, v in parts_ms.items()},
-               "api": "asb_upload_reads + asb_batch_begin/step + asb_batch_records_dev + NCCL gather + D2H on rank 0"}
+        tmp = a.tmpdir or tempfile_mod.mkdtemp(prefix="asb200_e2e_")
+        os.makedirs(tmp, exist_ok=True)
+        args = types.SimpleNamespace(outputfolder=tmp, similar_genes=80.0)
+        lists = [comparelist2_of(w) for _ in range(a.e2e_steps)]  # process_list sorts its batches in place: one fresh copy per step
+        stats = {}
+        region.begin()
+        for s in range(a.e2e_steps):
+            host.process_list(lists[s], "bench_compare.tmp", args, engine=facade, stats_out=stats)
+        t_e2e = region.end()
+        path = os.path.join(tmp, "bench_compare.tmp")
+        fbytes = os.path.getsize(path)
+        with open(path, "rb") as f:
+            crc = 0
+            while True:
+                blk = f.read(1 << 26)
+                if not blk:
+                    break
+                crc = zlib.crc32(blk, crc)
+        if not a.tmpdir:
+            shutil.rmtree(tmp, ignore_errors=True)
+        small = w["order"].nbytes + w["hi"].nbytes + w["dpass"].nbytes + w["drev"].nbytes
+        e2e = {"value": w["tl"] * a.e2e_steps / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": int((w["buf"].nbytes + w["offs"].nbytes + small) * world + sum(np.asarray(t).nbytes if not isinstance(t, bytes) else len(t) for t in w["tables"])),
+               "d2h_bytes_per_step": int(fbytes), "steps": a.e2e_steps, "ms_per_step": t_e2e / a.e2e_steps * 1e3,
+               "tempfile_bytes": int(fbytes), "tempfile_crc32": crc,
+               "api": "host.process_list(comparelist2, tempfile) -- the drop-in for amplicon_sorter.py:647 -- "
+                      + ("on one Engine" if world == 1 else f"on dist.ShardedEngine over {world} ranks (NCCL broadcast of the job, per-slab device-side gather)")
+                      + ": str join + H2D of the reads, all slabs, text assembled on the GPU, D2H, write(2) on a writer thread"}
+    known = KNOWN_TEXT_CRC.get(a.config) if a.scale == 1.0 else None
+    if crc is not None and known is not None:
+        parity["records_crc"] = crc
+        parity["records_crc_check"] = "ok" if crc == known else f"FAILED (expected {known})"
+    elif crc is not None:
+        parity["records_crc"] = crc
 
-    if rank == 0:
-        lop3, mix = eng.int_peak(4000)
-        screen_s = agg["screen_ms"] / 1e3
-        # asb_screen alone: its own word-update counter over its own launch durations (CUDA events in the library)
-        wu_rate = agg["screen_word_updates"] / max(screen_s, 1e-9)
-        achieved = wu_rate * ALU_OPS_PER_WORD_UPDATE / 1e12
-        peak = max(lop3, mix)
-        roofline = {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "Tops/s (INT32 ALU-pipe lane-ops)",
-                    "frac": achieved / peak if peak else None, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                    "kernel": "asb_screen", "launches": agg["screen_launches"],
-                    "avg_launch_ms": agg["screen_ms"] / max(agg["screen_launches"], 1),
-                    "kernel_share_of_step": screen_s / max(agg["total_ms"] / 1e3, 1e-9),
-                    "word_updates_per_s": wu_rate, "alu_ops_per_word_update": ALU_OPS_PER_WORD_UPDATE,
-                    "word_updates_per_pair": agg["word_updates"] / max(agg["pairs"], 1),
-                    "peak_source": "asb_int_peak measured live on this GPU: best of LOP3-chain probe (%.2f) and LOP3/SHF/IADD3/LEA mix probe (%.2f); nominal 148 SM x 64 lanes x 1.965 GHz = 18.61" % (lop3, mix),
-                    "ncu": "profiles/r1_asb_screen_ncu_full_v7.txt: sm__inst_executed_pipe_alu 91.4 % of peak, dram 48.7 MB per launch",
-                    "nominal": {"ops_per_job": nominal_ops(w), "note": "SURVEY 8(d): 20*ceil(m/32)*n*2 per pair (full-matrix Myers, both strands)",
-                                "equivalent_tops": nominal_ops(w) * a.steps / t_res / 1e12 / max(world, 1)},
-                    "hbm": {"peak_gbs": _measured_peak("hbm_gbs"), "note": "path is not HBM-bound: ~200 MB of symbol codes stay L2-resident"}}
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": t_res / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "u32", "data": "synthetic",
-                "config": {"workload": f"cfg5: --all on {w['n_reads']} synthetic ~1 kb reads (200 templates, 6% ONT-like error, both strands, 1% with N), -sg 80; one step = the whole {w['tl']}-pair job",
-                           "reads": w["n_reads"], "pairs_per_step": w["tl"], "records_per_step": n_records, "mean_read_len": w["mean_len"],
-                           "l2_policy": ("inputs (2 x %.0f MB symbol codes) exceed the 126 MB L2; no flush needed" % (w["buf"].nbytes / 1e6)) if flush_buf is None
-                           else "inputs fit in L2: a 192 MB buffer is overwritten between timed steps",
-                           "sharding": "rows of the length-sorted batch dealt cyclically over ranks; NCCL gather of records to rank 0"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline}
-        if not a.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(w, seconds=a.cpu_seconds) if world == 1 else None
-        print(json.dumps(line), file=_OUT, flush=True)
-    eng.close()
+    lop3, mix = eng.int_peak(4000)
+    screen_s = agg["screen_ms"] / 1e3 / world  # rank-sum of device times -> mean per rank
+    total_s = agg["total_ms"] / 1e3 / world
+    wu_rate = agg["screen_word_updates"] / max(screen_s, 1e-9) / world  # per GPU
+    achieved = wu_rate * ALU_OPS_PER_WORD_UPDATE / 1e12
+    useful = agg["screen_useful_word_updates"] / max(agg["screen_word_updates"], 1)
+    peak = max(lop3, mix)
+    traffic = _ncu_traffic(a.config)
+    roofline = {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "Tops/s (INT32 ALU-pipe lane-ops, per GPU)",
+                "frac": achieved / peak if peak else None,
+                "achieved_useful": achieved * useful, "frac_useful": achieved * useful / peak if peak else None,
+                "live_lane_fraction": useful,
+                "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
+                "kernel": "asb_screen", "launches": agg["steps"],
+                "avg_launch_ms": agg["screen_ms"] / max(agg["steps"], 1) / world,
+                "kernel_share_of_step": screen_s / max(t_res, 1e-9),
+                "kernel_share_of_device_time": screen_s / max(total_s, 1e-9),
+                "word_updates_per_s": wu_rate, "alu_ops_per_word_update": ALU_OPS_PER_WORD_UPDATE,
+                "word_updates_per_pair": agg["word_updates"] / max(agg["pairs"], 1),
+                "useful_word_updates_per_pair": agg["useful_word_updates"] / max(agg["pairs"], 1),
+                "note": "achieved counts EXECUTED lane-slots (32 lanes x active words x columns of every warp); achieved_useful only the "
+                        "words each lane itself still needed (live_lane_fraction = useful / executed, counted by the kernel)",
+                "peak_source": "asb_int_peak measured live on this GPU: best of LOP3-chain probe (%.2f) and LOP3/SHF/IADD3/LEA mix probe (%.2f); nominal 148 SM x 64 lanes x 1.965 GHz = 18.61" % (lop3, mix),
+                "nominal": {"ops_per_job": nominal_ops(w), "note": "SURVEY 8(d): 20*ceil(m/32)*n*2 per pair (full-matrix Myers, both strands)",
+                            "equivalent_tops": nominal_ops(w) * a.steps / t_res / 1e12 / max(world, 1)},
+                "hbm": {"peak_gbs": _measured_peak("hbm_gbs"), "note": "path is not HBM-bound: ~200 MB of symbol codes stay L2-resident"}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": t_res / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"{DESCR[a.config]}, -sg 80; one step = the whole {w['tl']}-pair job",
+                       "reads": w["n_reads"], "pairs_per_step": w["tl"], "records_per_step": n_records, "mean_read_len": w["mean_len"],
+                       "l2_policy": ("inputs (2 x %.0f MB symbol codes) exceed the 126 MB L2; no flush needed" % (w["buf"].nbytes / 1e6)) if flush_buf is None
+                       else "inputs fit in L2: a 192 MB buffer is overwritten between timed steps",
+                       "sharding": "rows of the length-sorted batch dealt cyclically over ranks; per-slab NCCL gather of the records to rank 0 (dist.gather_step)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, **parity}
+    if not a.no_cpu and world == 1:
+        line["cpu_baseline"] = cpu_baseline(w, seconds=a.cpu_seconds)
+        ref = _reference_script_record()
+        if ref:
+            line["cpu_baseline"]["reference_script"] = ref
+    print(json.dumps(line), file=_OUT, flush=True)
+    failed = parity.get("parity_check") == "FAILED" or str(parity.get("records_crc_check", "ok")).startswith("FAILED")
+    facade.close()
     if world > 1:
-        dist.destroy_process_group()
+        torch.distributed.destroy_process_group()
+    if failed:
+        raise SystemExit("bench.py: PARITY FAILED -- the numbers above are void")
 
 
 def _measured_peak(key):
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return json.load(f).get(key)
+    except Exception:
+        return None
+
+
+def _ncu_traffic(cfg):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE asb_screen launch of this config's full-size job, from an
+    `ncu --set full` capture (profiles/r2_traffic.json records the command and the report it came from)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            return json.load(f).get(f"cfg{cfg}")
     except Exception:
         return None
 

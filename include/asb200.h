@@ -55,6 +55,11 @@ typedef struct {
     uint32_t launches;       /* this library's own kernels launched by the step (cub sorts not counted) */
     uint32_t reserved;
     uint64_t screen_word_updates; /* the part of word_updates executed by asb_screen alone */
+    /* word_updates counts EXECUTED lane-slots: the 32 lanes of a warp share one code path, so a lane that is idle,
+     * already decided, or needs fewer words than its neighbours still executes.  useful_* counts only the words each
+     * lane itself still needed (see band_pass): the ratio is the live-lane occupancy of the executed work. */
+    uint64_t useful_word_updates;
+    uint64_t screen_useful_word_updates;
 } asb_step_info;
 
 /* Replaces nothing in the reference (it has no device): create/destroy an engine on `device`.
@@ -94,6 +99,27 @@ int asb_batch_records(asb_ctx *ctx, asb_record *dst);
 int64_t asb_format_records(const asb_record *recs, uint64_t n, const uint32_t *idx_sorted, const uint32_t *len_sorted,
                            const uint64_t *lbase, uint32_t lbase_len, const uint32_t *soff, uint64_t n_strings,
                            const char *sbuf, char *out, uint64_t cap);
+
+/* ---- the tempfile as TEXT, assembled on the device (amplicon_sorter.py:792-798 builds the lines, :802-807 appends
+ * them to <stem>_compare.tmp).  asb_text_begin ships, for the batch of asb_batch_begin: idx_sorted[p] = the idx field
+ * (:560-561) printed for sorted position p, and the caller's iden strings -- Python's own str(round(1 - d/L, 3)) --
+ * string number lbase[L] + d at sbuf[soff[e] .. soff[e+1]) (lbase[L] = 0xFFFFFFFF: no string for that length) with
+ * milli[e] = iden * 1000.  It also empties the context's resident line set (asb_lines_*): a new tempfile starts.
+ * asb_text_step turns sorted records into lines "idxA:idxB:iden[:reverse]\n" in (i_pos, j_pos) order, copies the text
+ * to host_dst (cap bytes; pinned memory from asb_host_alloc makes the copy asynchronous-capable) and APPENDS the same
+ * lines in integer form to the resident line set, so SSG / the best-hit filters run without parsing the file.
+ *   dev_recs == NULL : the records of the last asb_batch_step (already sorted);
+ *   dev_recs != NULL : n records in DEVICE memory, e.g. the NCCL gather of several ranks' lists; sort != 0 orders them. */
+int asb_text_begin(asb_ctx *ctx, const uint32_t *idx_sorted, uint32_t n_pos, const uint32_t *lbase, uint32_t lbase_len,
+                   const uint32_t *soff, const uint16_t *milli, uint32_t n_strings, const char *sbuf, uint32_t sbuf_len);
+int asb_text_step(asb_ctx *ctx, const asb_record *dev_recs, uint64_t n, int sort, char *host_dst, uint64_t cap,
+                  uint64_t *nbytes);
+/* Pinned host memory for the text (no context needed). */
+int asb_host_alloc(uint64_t bytes, void **out);
+void asb_host_free(void *p);
+/* The resident line set: number of lines, and a copy to the host (any destination may be NULL). */
+uint64_t asb_lines_count(const asb_ctx *ctx);
+int asb_lines_fetch(asb_ctx *ctx, uint32_t *a, uint32_t *b, uint32_t *milli, uint8_t *rev);
 
 /* Same, into DEVICE memory on the context's device (for an NCCL gather of the per-GPU lists). */
 int asb_batch_records_dev(asb_ctx *ctx, asb_record *dev_dst);

@@ -278,12 +278,16 @@ typedef struct {
  *               2 = plain DP (ground truth, slow)
  *   row_begin/row_end/row_step : restrict to rows i in [row_begin,row_end) with stride row_step
  *               (bounded samples for bench.py; a full run is 0, n, 1)
+ *   col_step  : of every sampled row keep the partners j = i + 1 + t * col_step (1 = all of them).  A 2-D strided
+ *               sample gives every host thread many rows of equal size: with rows only, a 20 s sample of a 100,000-read
+ *               job is a dozen rows of very different lengths, and the longest row is the wall time whatever the
+ *               thread count
  * Output records are in the reference's -np 1 order (i ascending, then j ascending).  Returns
  * the number of records, or -1 if cap is too small (stats are still filled).
  */
 typedef struct {
     const uint8_t *seqs; const uint64_t *offs; const uint32_t *order; uint32_t n;
-    double similarg; int algo; uint32_t row_begin, row_step, nrows;
+    double similarg; int algo; uint32_t row_begin, row_step, nrows, col_step;
     asref_record **rowrec; uint32_t *rowcnt;
     atomic_uint next_row;
     atomic_ullong pairs, rc;
@@ -311,7 +315,7 @@ static void *batch_worker(void *arg)
         bs = (int32_t *)realloc(bs, sizeof(int32_t) * (size_t)p.W);
         uint32_t cnt = 0, rcap_row = 0;
         asref_record *recs = NULL;
-        for (uint32_t j = i + 1; j < n; j++) {
+        for (uint32_t j = i + 1; j < n; j += J->col_step) {
             const uint8_t *A2 = J->seqs + J->offs[J->order[j]];
             int32_t ln = (int32_t)(J->offs[J->order[j] + 1] - J->offs[J->order[j]]);
             if ((double)m * 1.05 < (double)ln) continue; /* AS:679 */
@@ -365,7 +369,7 @@ int asref_host_threads(void) { return resolve_threads(0); }
 
 int64_t asref_process_batch(const uint8_t *seqs, const uint64_t *offs, const uint32_t *order, uint32_t n,
                             double similar_genes, int algo, uint32_t row_begin, uint32_t row_end,
-                            uint32_t row_step, asref_record *out, uint64_t cap, asref_stats *stats,
+                            uint32_t row_step, uint32_t col_step, asref_record *out, uint64_t cap, asref_stats *stats,
                             int nthreads)
 {
     batch_job J;
@@ -375,7 +379,7 @@ int64_t asref_process_batch(const uint8_t *seqs, const uint64_t *offs, const uin
     J.algo = algo;
     if (row_end > n) row_end = n;
     if (row_step == 0) row_step = 1;
-    J.row_begin = row_begin; J.row_step = row_step;
+    J.row_begin = row_begin; J.row_step = row_step; J.col_step = col_step ? col_step : 1;
     J.nrows = row_end > row_begin ? (row_end - row_begin + row_step - 1) / row_step : 0;
     J.rowrec = (asref_record **)calloc(J.nrows ? J.nrows : 1, sizeof(*J.rowrec));
     J.rowcnt = (uint32_t *)calloc(J.nrows ? J.nrows : 1, sizeof(uint32_t));

@@ -43,7 +43,7 @@ def lib():
         L.asref_iden.restype = C.c_double
         L.asref_host_threads.restype = C.c_int
         L.asref_process_batch.argtypes = [u8p, u64p, u32p, C.c_uint32, C.c_double, C.c_int, C.c_uint32, C.c_uint32,
-                                          C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(Stats), C.c_int]
+                                          C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(Stats), C.c_int]
         L.asref_process_batch.restype = C.c_int64
         L.asref_format_lines.argtypes = [C.c_void_p, C.c_uint64, u32p, u32p, u64p, C.c_char_p, C.c_uint64]
         L.asref_format_lines.restype = C.c_int64
@@ -100,8 +100,9 @@ def stable_length_order(lengths: np.ndarray) -> np.ndarray:
     return np.argsort(np.asarray(lengths), kind="stable").astype(np.uint32)
 
 
-def process_batch(seqs, offs, order, similar_genes=80.0, algo="myers", rows=None, nthreads=0, cap=None):
-    """One batch of process_list (AS:647-807).  Returns (records, stats dict)."""
+def process_batch(seqs, offs, order, similar_genes=80.0, algo="myers", rows=None, nthreads=0, cap=None, col_step=1):
+    """One batch of process_list (AS:647-807).  Returns (records, stats dict).
+    rows = (begin, end, step) and col_step restrict the run to a strided sample of the pair set (bench.py)."""
     order = np.ascontiguousarray(order, dtype=np.uint32)
     n = order.shape[0]
     rb, re_, rs = rows if rows is not None else (0, n, 1)
@@ -110,7 +111,7 @@ def process_batch(seqs, offs, order, similar_genes=80.0, algo="myers", rows=None
     while True:
         out = np.empty(cap, dtype=RECORD)
         r = lib().asref_process_batch(_p(seqs, C.c_uint8), _p(offs, C.c_uint64), _p(order, C.c_uint32), n,
-                                      float(similar_genes), ALGO[algo], rb, re_, rs, out.ctypes.data, cap,
+                                      float(similar_genes), ALGO[algo], rb, re_, rs, int(col_step), out.ctypes.data, cap,
                                       C.byref(st), nthreads)
         if r >= 0:
             break

@@ -44,33 +44,10 @@ def main():
     if a.stage == "gpu":
         launcher.install_gpu_stage(ns)
     elif a.stage == "oracle":
-        from amplicon_sorter_b200 import host
         from tests.fake_engine import OracleEngine
 
-        def process_list(self, tempfile):
-            return host.process_list(self, tempfile, ns["args"], engine=OracleEngine())
-
-        ns["process_list"] = process_list
-
-        def process_consensuslist(indexes, grouplist, group_filename):
-            return host.process_consensuslist(indexes, grouplist, group_filename, args=ns["args"],
-                                              comparelist2=ns["comparelist2"], similar=ns["similar"], engine=OracleEngine())
-
-        if "process_consensuslist" in os.environ.get("ASB200_STAGES", "process_list,process_consensuslist"):
-            ns["process_consensuslist"] = process_consensuslist
-        if "iden_consensus" in os.environ.get("ASB200_STAGES", "iden_consensus"):
-            original_do_parallel = ns["do_parallel"]
-
-            def do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename):
-                if getattr(worker, "__name__", "") != "iden_consensus":
-                    return original_do_parallel(outputfolder, nprocesses, consensus_tempfile, worker, stringx, group_filename)
-                return host.iden_consensus_files(outputfolder, consensus_tempfile, stringx, engine=OracleEngine())
-
-            ns["do_parallel"] = do_parallel
-
-        if "groups" in os.environ.get("ASB200_STAGES", "groups"):
-            shared = OracleEngine()
-            launcher.install_group_stage(ns, lambda: shared)
+        shared = OracleEngine()  # the CPU oracle behind the engine interface: the product's host code, no GPU
+        launcher.install_gpu_stage(ns, engine_factory=lambda: shared)
 
     inner_pl = ns["process_list"]
     inner_sg = ns["sort_groups"]

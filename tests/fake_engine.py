@@ -3,12 +3,70 @@
 import numpy as np
 
 from amplicon_sorter_b200._ffi import RECORD
+from amplicon_sorter_b200.engine import EngineBase, TextChunk
 from oracle import oracle
 
 
-class OracleEngine:
+class OracleEngine(EngineBase):
     def __init__(self):
         self.closed = False
+        self._lines_token = None
+        self._res = [np.zeros(0, np.uint32)] * 3 + [np.zeros(0, bool)]
+
+    # batch_begin / batch_step / text_begin / text_step: the stepping interface of Engine, one slab per batch
+    def batch_begin(self, order, hi, dpass, drev, rank=0, world=1):
+        self._batch = (np.asarray(order, np.uint32), np.asarray(hi, np.uint32), np.asarray(dpass, np.uint32), np.asarray(drev, np.uint32), rank, world)
+        self._stepped = False
+
+    def batch_step(self):
+        if self._stepped:
+            return None
+        self._stepped = True
+        self._recs, tot = self.compare_batch(*self._batch)
+        return dict(tot, launches=0, screen_word_updates=0)
+
+    def batch_records(self, n):
+        return self._recs
+
+    def step_records_tensor(self, n_records, dev):
+        import torch
+
+        return torch.from_numpy(self._recs.view(np.uint32).reshape(-1, 4).view(np.int32).copy()).to(dev)
+
+    def text_begin(self, idx_sorted, lbase, soff, milli, sbuf):
+        self._tabs = (np.asarray(idx_sorted), np.asarray(lbase), np.asarray(soff), np.asarray(milli), bytes(sbuf))
+        self._lens_sorted = (self.offs[1:] - self.offs[:-1]).astype(np.int64)[self._batch[0]]
+        self._res = [np.zeros(0, np.uint32)] * 3 + [np.zeros(0, bool)]
+        self._lines_token = None
+
+    def text_step(self, n_records, dev_ptr=None, sort=False):
+        assert dev_ptr is None
+        return self._format(self._recs)
+
+    def text_step_tensor(self, recs, sort=True):
+        r = recs.cpu().numpy().view(np.uint32).reshape(-1).view(RECORD)
+        if sort:
+            key = r["i_pos"].astype(np.uint64) << np.uint64(32) | r["j_pos"].astype(np.uint64)
+            r = r[np.argsort(key, kind="stable")]
+        return self._format(r)
+
+    def _format(self, recs):
+        idx, lbase, soff, milli, sbuf = self._tabs
+        out, a, b, m, rv = [], [], [], [], []
+        for i, j, d, rev in recs.tolist():
+            e = int(lbase[self._lens_sorted[j]]) + d
+            assert lbase[self._lens_sorted[j]] != 0xFFFFFFFF and e < milli.shape[0]
+            out.append(b"%d:%d:%s%s\n" % (idx[i], idx[j], sbuf[soff[e]:soff[e + 1]], b":reverse" if rev else b""))
+            a.append(idx[i]); b.append(idx[j]); m.append(milli[e]); rv.append(bool(rev))
+        self._res = [np.concatenate([x, np.asarray(y, dtype=x.dtype)]) for x, y in zip(self._res, (a, b, m, rv))]
+        self._lines = tuple(self._res[:3])  # the printed lines are the resident line set
+        return TextChunk(b"".join(out))
+
+    def lines_count(self):
+        return int(self._res[0].shape[0])
+
+    def lines_fetch(self):
+        return tuple(self._res)
 
     def upload_reads(self, buf, offs):
         self.buf = np.ascontiguousarray(buf, dtype=np.uint8)
@@ -90,8 +148,10 @@ class OracleEngine:
 
     # consumers of <stem>_compare.tmp: the C restatements of oracle/asref.c behind the Engine methods
     def lines_upload(self, a, b, milli):
+        tok, self._lines_token = self._lines_token, None
+        if tok is not None and hasattr(tok, "materialize"):
+            tok.materialize()
         self._lines = (np.asarray(a, np.uint32), np.asarray(b, np.uint32), np.asarray(milli, np.uint32))
-        self._lines_token = None
 
     def lines_hist(self):
         return np.bincount(self._lines[2], minlength=1001).astype(np.uint64), 0.0

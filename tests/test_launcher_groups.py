@@ -223,3 +223,46 @@ def test_launcher_fails_loudly_without_an_engine(tmp_path, monkeypatch):
     with pytest.raises(SystemExit) as e:
         launcher.main(["--script", str(script), "-i", "x.fastq"])
     assert "cannot start the CUDA engine" in str(e.value)
+
+
+def test_stage_errors_are_not_swallowed_by_the_reference(tmp_path, capsys):
+    """an engine failure inside a replaced stage must not become a silently skipped input file.  The
+    reference's main loop catches Exception (amplicon_sorter.py:2184); `loud` turns the failure into SystemExit."""
+    from amplicon_sorter_b200 import host
+    from amplicon_sorter_b200._ffi import EngineError
+
+    class Broken(OracleEngine):
+        def upload_reads(self, buf, offs):
+            raise EngineError(-3, "out of memory (injected)")
+
+    script = tmp_path / "stub.py"
+    script.write_text("import types\nargs = types.SimpleNamespace(outputfolder=%r, similar_genes=80.0)\n"
+                      "def process_list(self, tempfile):\n    pass\n\ndef do_parallel(*a):\n    pass\n\n"
+                      "if __name__ == '__main__':\n    for f in (1, 2):\n        try:\n            process_list(BATCHES, 'x_compare.tmp')\n"
+                      "        except Exception:\n            continue\n" % str(tmp_path))
+    ns, main_code = launcher.load_reference(str(script))
+    ns["BATCHES"] = [[["a", "ACGT" * 100, "u", 0], ["b", "ACGT" * 100, "u", 1]]]
+    launcher.install_gpu_stage(ns, engine_factory=lambda: Broken(), stages={"process_list"})
+    with pytest.raises(SystemExit) as e:
+        launcher.execute(ns, main_code, [])
+    assert "process_list failed" in str(e.value)
+    assert "out of memory (injected)" in capsys.readouterr().err
+    # ... while the reference's own "nothing to compare" protocol still skips the file quietly (:702-706, :768-772)
+    ns["BATCHES"] = [[["a", "A" * 300, "u", 0], ["b", "C" * 400, "u", 1]]]
+    open(tmp_path / "results.txt", "w").close()
+    launcher.install_gpu_stage(ns, engine_factory=lambda: OracleEngine(), stages={"process_list"})
+    launcher.execute(ns, main_code, [])
+    assert "No reads to compare" in open(tmp_path / "results.txt").read()
+    assert host.NoReadsToCompare.__mro__[1] is Exception
+
+
+def test_stage_selection_is_parsed_once(monkeypatch):
+    monkeypatch.delenv("ASB200_STAGES", raising=False)
+    assert launcher.enabled_stages() == set(launcher.ALL_STAGES)
+    monkeypatch.setenv("ASB200_STAGES", "process_list, iden_consensus")
+    assert launcher.enabled_stages() == {"process_list", "iden_consensus"}  # independent of process_consensuslist
+    monkeypatch.setenv("ASB200_STAGES", "process_list,process_consensuslist")
+    assert launcher.enabled_stages() == {"process_list", "process_consensuslist"}
+    monkeypatch.setenv("ASB200_STAGES", "proces_list")
+    with pytest.raises(SystemExit):
+        launcher.enabled_stages()
