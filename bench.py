@@ -51,7 +51,7 @@ ALU_OPS_PER_WORD_UPDATE = 10  # ALU-pipe instructions per Myers word-update in a
 # sampled rows matched the oracle (tests/test_gpu_fullsize.py); every later run -- any kernel version, any number of
 # GPUs -- must reproduce it.  None = no constant recorded for that config yet (the run prints its CRC).
 KNOWN_TEXT_CRC = {
-    5: None,
+    5: 1976580653,  # 24,887,125 lines, 539,029,280 bytes (r2, 1 x B200; same line count as every r1 kernel version)
 }
 DESCR = {
     1: "cfg1: default batch mode on 1,000 synthetic ~700 bp reads (5 templates)",

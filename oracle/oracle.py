@@ -165,13 +165,22 @@ def py_lev(a: str, b: str) -> int:
     return prev[-1]
 
 
-def py_distance(X1: str, X2: str) -> float:
+def c_lev(a: str, b: str) -> int:
+    """The same textbook DP, compiled (asref_dp_nw): for restatement runs on fixture-sized inputs."""
+    return nw(a.encode("latin-1"), b.encode("latin-1"), "dp")
+
+
+def c_hw(q: str, t: str) -> int:
+    return hw(q.encode("latin-1"), t.encode("latin-1"))
+
+
+def py_distance(X1: str, X2: str, lev=py_lev) -> float:
     """distance() AS:224-234 with edlib replaced by the DP definition."""
     if len(X1) > len(X2):
         A2, A1 = X1, X2
     else:
         A1, A2 = X1, X2
-    d = py_lev(A1, A2)
+    d = lev(A1, A2)
     return round(1 - d / len(A2), 3)
 
 
@@ -201,7 +210,7 @@ def py_process_list(batches, similar_genes=80.0):
     return lines
 
 
-def py_process_consensuslist(indexes, grouplist, comparelist2, similar):
+def py_process_consensuslist(indexes, grouplist, comparelist2, similar, lev=py_lev):
     """process_consensuslist AS:1627-1690 + similarity_species AS:1692-1715 at -np 1 -> list of lines
     (None when the reference would not run the comparison at all: empty last spool chunk, AS:1687)."""
     indexes2 = indexes.copy()
@@ -227,11 +236,11 @@ def py_process_consensuslist(indexes, grouplist, comparelist2, similar):
         return None
     lines = []
     for A1, A2 in todo:
-        iden = py_distance(A1[1], A2[1])
+        iden = py_distance(A1[1], A2[1], lev)
         if iden >= similar - 0.01:
             lines.append(str(A1[3]) + ":" + str(A2[0]) + ":" + str(iden))
         elif iden < 0.5:
-            iden = py_distance(A1[1], py_compl_reverse(A2[1]))
+            iden = py_distance(A1[1], py_compl_reverse(A2[1]), lev)
             if iden >= similar - 0.01:
                 lines.append(str(A1[3]) + ":" + str(A2[0]) + ":" + str(iden))
     return lines
@@ -250,11 +259,13 @@ def py_hw(q: str, t: str) -> int:
     return best
 
 
-def py_iden_consensus(todolist):
+def py_iden_consensus(todolist, hw_fn=None):
     """iden_consensus AS:1139-1158 -> lines 'y,z,iden' (distance() with mode='HW', AS:224-234)."""
+    hw_fn = hw_fn or py_hw
+
     def dist_hw(X1, X2):
         A1, A2 = (X2, X1) if len(X1) > len(X2) else (X1, X2)
-        return round(1 - py_hw(A1, A2) / len(A2), 3)
+        return round(1 - hw_fn(A1, A2) / len(A2), 3)
 
     lines = []
     for A1, A2, y, z in todolist:

@@ -147,3 +147,65 @@ def test_hw_distance_pairs(engine):
     fe.upload_reads(buf, offs)
     want = fe.distance_pairs(a, b, strand, mode="HW")
     assert np.array_equal(got, want)
+
+
+# ---- pinned to the reference: fixtures written by the UNMODIFIED process_consensuslist / similarity_species / do_parallel /
+# ---- iden_consensus (tests/golden/make_golden_stages.py, run where /root/reference exists)
+import glob  # noqa: E402
+import gzip  # noqa: E402
+import json  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+F1 = sorted(glob.glob(os.path.join(GOLD, "s_consensuslist_*.json.gz")))
+F2 = sorted(glob.glob(os.path.join(GOLD, "s_iden_consensus_*.json.gz")))
+
+
+def _load(path):
+    with gzip.open(path, "rt") as f:
+        return json.load(f)
+
+
+def _f1_case(fx):
+    return set(fx["indexes"]), [list(g) for g in fx["grouplist"]], [list(r) for r in fx["comparelist2"]]
+
+
+def test_stage_fixtures_present():
+    assert len(F1) == 3 and len(F2) == 2
+    assert {_load(p)["similar"] for p in F1} == {0.95, 0.94, 0.88}
+    for p in F1 + F2:
+        assert "unmodified" in _load(p)["reference"]
+
+
+@pytest.mark.parametrize("path", F1, ids=[os.path.basename(p) for p in F1])
+def test_reference_group_tmp_oracle_and_host(path, tmp_path):
+    """CPU: the restatement (pins the oracle) and the product's host code on the oracle-backed engine reproduce the
+    <group>.tmp the unmodified reference wrote."""
+    fx = _load(path)
+    want = fx["group_tmp"].splitlines()
+    assert len(want) > 50 and any(len(line.split(":")) == 3 for line in want)
+    assert oracle.py_process_consensuslist(*_f1_case(fx), fx["similar"], lev=oracle.c_lev) == want
+    assert run_host(OracleEngine(), _f1_case(fx), fx["similar"], tmp_path) == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", F1, ids=[os.path.basename(p) for p in F1])
+def test_reference_group_tmp_product(engine, path, tmp_path):
+    fx = _load(path)
+    assert run_host(engine, _f1_case(fx), fx["similar"], tmp_path) == fx["group_tmp"].splitlines()
+
+
+@pytest.mark.parametrize("path", F2, ids=[os.path.basename(p) for p in F2])
+def test_reference_consensus_tmp_oracle_and_host(path, tmp_path):
+    fx = _load(path)
+    want = fx["consensus_tmp"].splitlines()
+    todo = [list(e) for e in fx["todolist"]]
+    assert 20 < len(want) < len(todo)  # some pairs fall below 0.60 (:1151)
+    assert oracle.py_iden_consensus(todo, hw_fn=oracle.c_hw) == want
+    assert run_iden(OracleEngine(), todo, tmp_path) == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", F2, ids=[os.path.basename(p) for p in F2])
+def test_reference_consensus_tmp_product(engine, path, tmp_path):
+    fx = _load(path)
+    assert run_iden(engine, [list(e) for e in fx["todolist"]], tmp_path) == fx["consensus_tmp"].splitlines()
