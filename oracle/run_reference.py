@@ -18,6 +18,7 @@ import os
 import random
 import shutil
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -55,9 +56,12 @@ def main():
     def process_list_probe(self, tempfile):
         before = [[rec[3] for rec in d] for d in self]
         records = {str(rec[3]): rec[1] for d in self for rec in d}  # idx (:560-561) -> upper-cased SEQ (:551)
+        t0 = time.perf_counter()
         try:
             return inner_pl(self, tempfile)
         finally:
+            # wall time of the all-pairs stage alone (the reference's own stage includes >= 8 s of fixed sleeps)
+            print("ASB_TIMING process_list seconds=%.3f tl=%s" % (time.perf_counter() - t0, ns.get("tl")), flush=True)
             if a.dump:
                 os.makedirs(a.dump, exist_ok=True)
                 stem = os.path.basename(tempfile).replace("_compare.tmp", "")
