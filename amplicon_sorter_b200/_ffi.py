@@ -19,7 +19,9 @@ class StepInfo(C.Structure):
                 ("rc_survivors", C.c_uint64), ("zone_checks", C.c_uint64), ("word_updates", C.c_uint64),
                 ("row_begin", C.c_uint32), ("row_end", C.c_uint32), ("screen_ms", C.c_float), ("total_ms", C.c_float),
                 ("launches", C.c_uint32), ("reserved", C.c_uint32), ("screen_word_updates", C.c_uint64),
-                ("useful_word_updates", C.c_uint64), ("screen_useful_word_updates", C.c_uint64)]
+                ("useful_word_updates", C.c_uint64), ("screen_useful_word_updates", C.c_uint64),
+                ("pruned_pairs", C.c_uint64), ("cluster_ms", C.c_float), ("n_pivots", C.c_uint32),
+                ("lists_ms", C.c_float), ("reserved2", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

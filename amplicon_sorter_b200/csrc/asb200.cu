@@ -38,6 +38,7 @@ namespace asb {
 enum Counter : int { C_TASK = 0, C_F, C_R, C_Z, C_O, C_WORDS, C_ERR, C_USEFUL, C_COUNT };
 enum Mode : int { M_SCREEN = 0, M_FWD = 1, M_RC = 2, M_ZONE = 3, M_EXACT = 4 };
 enum DevErr : unsigned long long { E_BAND = 1ull, E_TABLE = 2ull, E_LIST = 4ull };
+constexpr int kRowBlock = 64;  // rows per block of the screen's task order (see DevBatch::my_rows)
 
 struct DevBatch {
     const uint8_t* codes_f;   // forward symbol codes, read regions 32-byte aligned + padded
@@ -52,10 +53,14 @@ struct DevBatch {
     uint64_t* F; uint64_t* R; uint64_t* Z; uint32_t* Zv; uint64_t* O; uint32_t* Ov;
     unsigned long long* ctr;  // [C_COUNT]
     uint64_t list_cap;
-    // screen task space
-    const uint32_t* grp_prefix;  // [rows+1] prefix of 32-target groups per row of the step
-    uint32_t row_begin, rows;
-    uint32_t n_tasks, rank, world;
+    // screen task space: this rank's rows of the step in blocks of kRowBlock; inside a block the tasks run
+    // group-major (all rows of the block against target group g, then g + 1, ...), so the ~35 KB of codes and seeds of
+    // a target group are read from HBM once per BLOCK of rows instead of once per row (the job's 460 MB of codes and
+    // seed tables do not fit the 126 MB L2: row-major order re-read them for every row, 66 GB per launch)
+    const uint32_t* my_rows;     // [n_my] sorted positions of this rank's rows with at least one partner
+    const uint32_t* blk_prefix;  // [n_blocks+1] first task of every row block
+    uint32_t n_my, n_blocks;
+    uint32_t n_tasks;
     int screen_cols_num;  // screen runs at most ceil(nmax * num / 256) columns
     int push_thresh;
     int cont_thresh;
@@ -63,6 +68,10 @@ struct DevBatch {
     const uint64_t* list; const uint32_t* list_val; uint64_t list_n;
     const uint8_t* ex_strand; int32_t* ex_out;  // M_EXACT
     int ex_hw;                                  // M_EXACT: 1 = edlib HW (infix) distance
+    int ex_cap;                                 // M_EXACT: < 0 = exact distance; >= 0 = exact if <= ex_cap, else -1 ("more than ex_cap")
+    // cluster pruning (see ensure_clusters): per READ a word (pivot, orientation, distance to it) and a matrix of lower
+    // bounds of the pivot x pivot distances in both relative orientations
+    const uint32_t* cword; const uint16_t* pivD; uint32_t n_piv;
     // seed lower bound (K2 put to work, see myers_band.cuh::SeedLB): per-read q-mer presence bitsets and the
     // seed codes of both strands, 8 per uint4 chunk, chunks of read r from seed_off[r]
     const uint32_t* qbits; const uint4* seeds_f; const uint4* seeds_r; const uint32_t* seed_off;
@@ -131,6 +140,7 @@ struct LaneJob {
     uint32_t zval;   // M_ZONE: d_rc carried by the entry
     uint64_t entry;  // M_EXACT: output slot
     int strand;      // M_EXACT
+    bool norc;       // M_FWD: the compl_reverse strand of this pair is already proven > dpass (cluster pruning)
 };
 
 // All lanes with valid==true share query `row`.  Runs the mode's passes and routes the results.
@@ -151,7 +161,7 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         tf = B.codes_f + off;
         tr = B.codes_r + off;
         const int L = n > m ? n : m;  // the cut-offs are indexed by the LONGER read (AS:233); all-pairs rows have n >= m
-        if (mode == M_EXACT) k = L;
+        if (mode == M_EXACT) k = B.ex_cap >= 0 ? min(L, B.ex_cap) : L;
         else if ((uint32_t)L >= B.table_len) { atomicOr(&B.ctr[C_ERR], (unsigned long long)E_TABLE); ok = false; }
         else if (mode == M_ZONE) k = (int)B.drev[L] - 1;
         else { const uint32_t kk = B.dpass[L]; k = kk == 0xFFFFFFFFu ? -1 : (int)kk; }
@@ -162,7 +172,7 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         const bool pass = ok && n <= k;
         if (mode == M_SCREEN || mode == M_FWD) warp_push(pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, ((uint32_t)n << 1), &B.ctr[C_ERR]);
         if (mode == M_ZONE) warp_push(job.valid && !pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, (job.zval << 1) | 1u, &B.ctr[C_ERR]);
-        if (mode == M_EXACT && job.valid) B.ex_out[job.entry] = B.ex_hw ? 0 : n;
+        if (mode == M_EXACT && job.valid) B.ex_out[job.entry] = B.ex_hw ? 0 : (n <= k ? n : -1);
         return;
     }
     // ---- warp-uniform band geometry covering every participating lane
@@ -174,6 +184,7 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
     const unsigned okm = __ballot_sync(0xFFFFFFFFu, ok);
     if (okm == 0u) {
         if (mode == M_ZONE) warp_push(job.valid, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, (job.zval << 1) | 1u, &B.ctr[C_ERR]);
+        if (mode == M_EXACT && job.valid) B.ex_out[job.entry] = -1;  // |n - m| > cap
         return;
     }
     BandGeom g;
@@ -207,7 +218,7 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
     // seed lower bound: the query's q-mer presence bitset goes next to its match masks
     SeedLB sl;
     sl.hs = nullptr; sl.J = 0;
-    const bool use_seeds = B.seed_on && mode != M_EXACT && mode != M_ZONE;
+    const bool use_seeds = B.seed_on && mode != M_ZONE && !(mode == M_EXACT && B.ex_cap < 0);
     uint32_t* qb = peq + B.peq_words;
     uint16_t* hs_lane = reinterpret_cast<uint16_t*>(qb + kSeedBitsPad) + (threadIdx.x & 31);
     const uint4* sf = nullptr;
@@ -240,7 +251,7 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         const bool surv = ok && st == PASS_SURVIVOR;
         if (phase == 0) {
             if (mode == M_EXACT) {
-                if (job.valid) B.ex_out[job.entry] = (st == PASS_DONE) ? sc : -1;
+                if (job.valid) B.ex_out[job.entry] = (ok && st == PASS_DONE && sc <= k) ? sc : -1;
                 return;
             }
             if (mode == M_ZONE) {  // emit the reverse record iff d_fwd > drev-1  (iden_fwd < 0.5, AS:794)
@@ -250,7 +261,7 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
             warp_push(pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, ((uint32_t)sc << 1), &B.ctr[C_ERR]);  // AS:791-793
             if (mode == M_SCREEN) warp_push(surv, B.F, nullptr, &B.ctr[C_F], B.list_cap, key, 0u, &B.ctr[C_ERR]);
             const bool need_rc = ok && !pass && !surv;  // proven d_fwd > dpass
-            if (mode == M_FWD) { warp_push(need_rc, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]); return; }
+            if (mode == M_FWD) { warp_push(need_rc && !job.norc, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]); return; }
             ok = need_rc;
             if (__ballot_sync(0xFFFFFFFFu, ok) == 0u) return;
         } else {
@@ -278,19 +289,21 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? 4 : 1) asb_screen(c
         if (lane == 0) t = atomicAdd(&B.ctr[C_TASK], 1ull);
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
         if (t >= B.n_tasks) break;
-        const uint32_t gidx = (uint32_t)t * B.world + B.rank;  // (world, rank) = (1, 0): the host deals whole rows
-        // row = last r with grp_prefix[r] <= gidx
-        uint32_t lo = 0, hi = B.rows;
+        // block = last b with blk_prefix[b] <= t
+        uint32_t lo = 0, hi = B.n_blocks;
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(&B.grp_prefix[mid]) <= gidx) lo = mid; else hi = mid;
+            if (__ldg(&B.blk_prefix[mid]) <= (uint32_t)t) lo = mid; else hi = mid;
         }
-        const uint32_t row = B.row_begin + lo;
-        const uint32_t gi = gidx - __ldg(&B.grp_prefix[lo]);
+        const uint32_t local = (uint32_t)t - __ldg(&B.blk_prefix[lo]);
+        const uint32_t r0 = lo * kRowBlock, nr = min((uint32_t)kRowBlock, B.n_my - r0);
+        const uint32_t gi = local / nr;
+        const uint32_t row = __ldg(&B.my_rows[r0 + local % nr]);
         LaneJob job;
         job.j = row + 1 + gi * 32 + lane;
         job.valid = job.j <= B.hi[row];
-        job.zval = 0; job.entry = 0; job.strand = 0;
+        job.zval = 0; job.entry = 0; job.strand = 0; job.norc = false;
+        if (__ballot_sync(0xFFFFFFFFu, job.valid) == 0u) continue;  // a shorter row of the block: no such group
         process_group<BT>(B, peq, M_SCREEN, row, job, cols_acc, useful_acc);
     }
     if (lane == 0 && cols_acc) atomicAdd(&B.ctr[C_WORDS], cols_acc);
@@ -327,7 +340,8 @@ __global__ void __launch_bounds__(256) asb_lists(const DevBatch B, const int mod
             const uint32_t row = __shfl_sync(0xFFFFFFFFu, myrow, __ffs(pm) - 1);
             LaneJob job;
             job.valid = pending && myrow == row;
-            job.j = (uint32_t)key;
+            job.j = (uint32_t)key & 0x7FFFFFFFu;
+            job.norc = ((uint32_t)key >> 31) != 0u;  // set by asb_prune on F entries
             job.zval = (mode == M_ZONE && have) ? B.list_val[e] : 0u;
             job.entry = e;
             job.strand = (mode == M_EXACT && have) ? (int)B.ex_strand[e] : 0;
@@ -338,6 +352,82 @@ __global__ void __launch_bounds__(256) asb_lists(const DevBatch B, const int mod
     if (lane == 0 && cols_acc) atomicAdd(&B.ctr[C_WORDS], cols_acc);
     const unsigned long long useful_warp = warp_sum_u64(useful_acc);
     if (lane == 0 && useful_warp) atomicAdd(&B.ctr[C_USEFUL], useful_warp);
+}
+
+// --------------------------------------------------------------------------------------------
+// asb_prune: cluster pruning of the pair set (the metric-space filter in front of the DP).
+//   Levenshtein distance is a metric and compl_reverse an isometry of it.  ensure_clusters() picked pivot reads
+//   and gave every read A a word (P_A, o_A, a): A lies within a <= kmax edits of pivot P_A taken in orientation
+//   o_A (0 = as uploaded, 1 = compl_reverse).  With lower bounds D[P][Q][x] of d(P, compl_reverse^x(Q)):
+//       d(A, B)                >= D[P_A][P_B][o_A ^ o_B]     - a - b
+//       d(A, compl_reverse(B)) >= D[P_A][P_B][o_A ^ o_B ^ 1] - a - b
+//   A pair whose bound exceeds dpass[len] on a strand needs no alignment on that strand: the reference would
+//   compute iden < similar_genes there (AS:791 / AS:796), whatever the exact value.  The bound never claims
+//   more: pairs it cannot decide go to the exact passes -- forward not proven -> F list (flag bit 31 of the
+//   column: compl_reverse strand already proven), forward proven -> R list unless that strand is proven too.
+//   The ':reverse' rule's own test (forward iden < 0.5, AS:794) is still decided exactly by the Z pass.
+//   Reads of unrelated amplicons sit ~0.52 L apart and reads of one amplicon ~0.12 L from their pivot, so on
+//   multi-amplicon data > 99 % of the pairs are decided here at a few instructions each.
+//   count_only: only count the survivors (sizes the lists before the real pass).
+// --------------------------------------------------------------------------------------------
+constexpr uint32_t kUncovered = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t cw_pivot(uint32_t w) { return w >> 20; }          // 12 bits
+__device__ __forceinline__ uint32_t cw_orient(uint32_t w) { return (w >> 19) & 1u; }  // 1 bit
+__device__ __forceinline__ uint32_t cw_dist(uint32_t w) { return w & 0x7FFFFu; }      // 19 bits
+
+__global__ void __launch_bounds__(256) asb_prune(const DevBatch B, const int count_only)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long nf = 0, nr = 0;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&B.ctr[C_TASK], 1ull);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= B.n_tasks) break;
+        uint32_t lo = 0, hi = B.n_blocks;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&B.blk_prefix[mid]) <= (uint32_t)t) lo = mid; else hi = mid;
+        }
+        const uint32_t local = (uint32_t)t - __ldg(&B.blk_prefix[lo]);
+        const uint32_t r0 = lo * kRowBlock, nrw = min((uint32_t)kRowBlock, B.n_my - r0);
+        const uint32_t gi = local / nrw;
+        const uint32_t row = __ldg(&B.my_rows[r0 + local % nrw]);
+        const uint32_t j = row + 1 + gi * 32 + lane;
+        bool needF = false, needR = false, pr = false;
+        if (j <= __ldg(&B.hi[row])) {
+            const int m = (int)__ldg(&B.pos_len[row]), n = (int)__ldg(&B.pos_len[j]);
+            const int L = n > m ? n : m;
+            int k = -1;
+            if ((uint32_t)L >= B.table_len) atomicOr(&B.ctr[C_ERR], (unsigned long long)E_TABLE);
+            else { const uint32_t kk = __ldg(&B.dpass[L]); k = kk == 0xFFFFFFFFu ? -1 : (int)kk; }
+            if (abs(n - m) <= k) {  // otherwise d >= |n - m| > k on both strands: nothing can be emitted
+                const uint32_t wa = __ldg(&B.cword[B.pos_read ? __ldg(&B.pos_read[row]) : row]);
+                const uint32_t wb = __ldg(&B.cword[B.pos_read ? __ldg(&B.pos_read[j]) : j]);
+                bool pf = false;
+                if (wa != kUncovered && wb != kUncovered) {
+                    const uint32_t x = cw_orient(wa) ^ cw_orient(wb);
+                    const uint16_t* d = B.pivD + ((size_t)cw_pivot(wa) * B.n_piv + cw_pivot(wb)) * 2;
+                    const int s = k + (int)cw_dist(wa) + (int)cw_dist(wb);
+                    pf = (int)__ldg(d + x) > s;
+                    pr = (int)__ldg(d + (x ^ 1u)) > s;
+                }
+                needF = !pf;
+                needR = pf && !pr;
+            }
+        }
+        if (count_only) { nf += needF; nr += needR; }
+        else {  // all 32 lanes take part in the warp-aggregated appends
+            const uint64_t key = ((uint64_t)row << 32) | j;
+            warp_push(needF, B.F, nullptr, &B.ctr[C_F], B.list_cap, key | (pr ? 0x80000000ull : 0ull), 0u, &B.ctr[C_ERR]);
+            warp_push(needR, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]);
+        }
+    }
+    if (count_only) {
+        nf = warp_sum_u64(nf); nr = warp_sum_u64(nr);
+        if (lane == 0 && nf) atomicAdd(&B.ctr[C_F], nf);
+        if (lane == 0 && nr) atomicAdd(&B.ctr[C_R], nr);
+    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -623,7 +713,7 @@ struct asb_ctx {
     uint32_t n = 0, rank = 0, world = 1, table_len = 0;
     std::vector<uint32_t> h_len, h_hi, h_dpass, h_drev;
     std::vector<uint32_t> h_pmax_dpass, h_pmax_drev;  // prefix maxima of the tables
-    DevBuf<uint64_t> d_pos_off; DevBuf<uint32_t> d_pos_len, d_hi, d_dpass, d_drev, d_grp;
+    DevBuf<uint64_t> d_pos_off; DevBuf<uint32_t> d_pos_len, d_hi, d_dpass, d_drev, d_grp, d_myrows;
     uint32_t next_row = 0;
     bool in_batch = false;
     // lists
@@ -632,7 +722,7 @@ struct asb_ctx {
     DevBuf<uint8_t> d_tmp;
     uint64_t list_cap = 0;
     unsigned long long* h_ctr = nullptr;  // pinned [C_COUNT]
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // last step's sorted records on device
     uint64_t* rec_keys = nullptr; uint32_t* rec_vals = nullptr; uint64_t rec_n = 0;
     uint32_t launches = 0;  // own kernels launched since the last step began
@@ -650,6 +740,13 @@ struct asb_ctx {
     DevBuf<uint64_t> d_t_keys, d_t_keys_alt, d_t_off;
     uint32_t t_n_pos = 0, t_lbase_len = 0, t_n_strings = 0;
     bool text_ready = false, lines_have_rev = false;
+    // cluster pruning (ensure_clusters): per-read cluster words, pivot x pivot lower bounds, and what the batch decided
+    DevBuf<uint32_t> d_cword, d_cl_u, d_cl_piv; DevBuf<uint16_t> d_pivD; DevBuf<uint64_t> d_cl_keys; DevBuf<uint8_t> d_cl_st; DevBuf<int32_t> d_cl_out;
+    int prune = 1;              // parameter "prune": 0 = never
+    uint32_t prune_min_reads = 1024; uint64_t prune_min_pairs = 1ull << 22;  // below these a job is a few milliseconds anyway
+    bool cl_ready = false; uint32_t cl_kmax = 0, cl_npiv = 0, cl_covered = 0;
+    int prune_mode = 0;         // this batch: 0 = undecided, 1 = prune path, -1 = screen path
+    float cl_ms = 0.f;          // device + host time spent building the clusters (reported with the first step)
 };
 
 namespace {
@@ -677,6 +774,12 @@ __global__ void asb_pack_records(const uint64_t* __restrict__ keys, const uint32
         asb_record r; r.i_pos = (uint32_t)(k >> 32); r.j_pos = (uint32_t)k; r.d = v >> 1; r.reverse = v & 1u;
         out[i] = r;
     }
+}
+
+unsigned grid_for(const asb_ctx* ctx, uint64_t n, int block)
+{
+    const uint64_t blocks = (n + block - 1) / block;
+    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 16));
 }
 
 int bits_for(uint32_t n) { int b = 0; while ((1ull << b) < (uint64_t)n + 1) ++b; return b; }
@@ -827,6 +930,213 @@ int ensure_seeds(asb_ctx* ctx)
 
 }  // namespace
 
+
+// --------------------------------------------------------------------------------------------
+// cluster pruning, host side
+// --------------------------------------------------------------------------------------------
+namespace asb {
+
+// entries ((p * 2 + s) * nu + u): key = (piv[p] << 32 | reads[u]), strand s -- every warp of the list kernel sees one
+// query (the pivot) and consecutive targets
+__global__ void __launch_bounds__(256) asb_cl_gen_kernel(const uint32_t* __restrict__ piv, uint32_t np, const uint32_t* __restrict__ reads, uint32_t nu,
+                                                       uint64_t* __restrict__ keys, uint8_t* __restrict__ st)
+{
+    const uint64_t total = (uint64_t)np * 2 * nu;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t u = (uint32_t)(e % nu);
+        const uint32_t ps = (uint32_t)(e / nu);
+        keys[e] = ((uint64_t)piv[ps >> 1] << 32) | reads[u];
+        st[e] = (uint8_t)(ps & 1u);
+    }
+}
+
+// per uncovered read: the closest of the np new pivots (either orientation) within the cap -> its cluster word
+__global__ void __launch_bounds__(256) asb_cl_assign_kernel(const int32_t* __restrict__ out, const uint32_t* __restrict__ reads, uint32_t nu, uint32_t np,
+                                                          uint32_t piv_base, uint32_t* __restrict__ cword)
+{
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
+        uint32_t best = kUncovered;
+        int bd = 0x7FFFFFFF;
+        for (uint32_t ps = 0; ps < 2 * np; ++ps) {
+            const int d = out[(uint64_t)ps * nu + u];
+            if (d >= 0 && d < bd) { bd = d; best = ((piv_base + (ps >> 1)) << 20) | ((ps & 1u) << 19) | (uint32_t)d; }
+        }
+        if (best != kUncovered) cword[reads[u]] = best;
+    }
+}
+
+// int32 capped distances ((p * 2 + x) * m + q) -> u16 lower bounds, "more than the cap" = cap + 1
+__global__ void __launch_bounds__(256) asb_cl_matrix_kernel(const int32_t* __restrict__ out, uint64_t total, uint32_t cap, uint16_t* __restrict__ D)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x)
+        D[e] = (uint16_t)(out[e] >= 0 ? (uint32_t)out[e] : cap + 1u);
+}
+
+}  // namespace asb
+
+namespace {
+
+constexpr uint32_t kClMaxPivots = 1024;   // 12 bits in the cluster word would allow 4095; the pivot matrix is m x m x 2 alignments
+constexpr uint32_t kClRound = 64;         // candidate pivots per round
+
+// Capped exact distances of the entries (keys[e] = query << 32 | target read id, st[e] = target strand) already in
+// DEVICE memory: out[e] = d if d <= cap, else -1.  Positions are read ids (the batch's own arrays stay untouched).
+// need = window words a warp of 32 consecutive entries can ask for (0 = the bound that holds for ANY mix of lengths:
+// one lane's band may hang below the diagonal and another's above it, each by up to `cap` rows).
+int capped_exact_dev(asb_ctx* ctx, const uint64_t* d_keys, const uint8_t* d_st, uint64_t n_entries, int cap, int32_t* d_out, int need)
+{
+    if (n_entries == 0) return ASB_OK;
+    const int Wmax = (int)((ctx->max_len + 31) / 32);
+    if (need <= 0) need = 2 * ((cap + 31) / 32) + 1;
+    const int cls = class_for(std::min(need, std::max(Wmax, 1)));
+    DevBatch B;
+    memset(&B, 0, sizeof B);
+    B.codes_f = ctx->d_cf.p; B.codes_r = ctx->d_cr.p; B.pos_off = ctx->d_roff_all.p; B.pos_len = ctx->d_rlen_all.p;
+    B.n = ctx->n_reads; B.sigma = ctx->sigma; B.ctr = ctx->d_ctr.p; B.ex_strand = d_st; B.ex_out = d_out; B.ex_hw = 0; B.ex_cap = cap;
+    set_layout(ctx, B, peq_stride(Wmax, kClasses[cls]), true);
+    CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
+    int rc = run_list(ctx, B, M_EXACT, cls, const_cast<uint64_t*>(d_keys), nullptr, n_entries);
+    if (rc) return rc;
+    return read_counters(ctx);
+}
+
+// Window words of one warp whose 32 targets have lengths n_lo..n_hi against a query of length m at threshold cap
+// (process_group's geometry: D = e + max(n - m, 0), E = e + max(m - n, 0), e = (k - |n - m|) / 2, lanes with |n - m| > k idle).
+int slice_need(int m, int n_lo, int n_hi, int cap)
+{
+    int Dmax = 0, Emax = 0;
+    const int pts[3] = {n_lo, n_hi, std::min(std::max(m, n_lo), n_hi)};
+    for (int x = 0; x < 3; ++x) {
+        // the extremes of D and E over [n_lo, n_hi] sit at its ends, at n = m, or where a lane drops out (|n - m| = k)
+        for (int n : {pts[x], std::min(std::max(m - cap, n_lo), n_hi), std::min(std::max(m + cap, n_lo), n_hi)}) {
+            const int k = std::min(std::max(n, m), cap), dl = std::abs(n - m);
+            if (dl > k) continue;
+            const int e = (k - dl) >> 1;
+            Dmax = std::max(Dmax, e + std::max(n - m, 0));
+            Emax = std::max(Emax, e + std::max(m - n, 0));
+        }
+    }
+    return ((Dmax + 31) >> 5) + ((Emax + 31) >> 5) + 1;
+}
+
+// Picks pivot reads and assigns every read it can to a pivot (see asb_prune).  Deterministic: same reads, same kmax
+// -> same clusters on every rank.  Rounds: sample candidates among the reads no pivot covers yet, drop candidates
+// that another candidate of the round covers, align the uncovered reads against the new pivots (both strands,
+// threshold kmax: as cheap as one row of the all-pairs job per pivot), repeat until (almost) every read is covered,
+// the pivot budget is used up, or a round stops paying (no cluster structure: the batch then runs without pruning).
+int ensure_clusters(asb_ctx* ctx, uint32_t kmax)
+{
+    if (ctx->cl_ready && ctx->cl_kmax == kmax) return ASB_OK;
+    ctx->cl_ready = false; ctx->cl_npiv = 0; ctx->cl_covered = 0;
+    const uint32_t n = ctx->n_reads;
+    if (3ull * kmax + 1 > 65535ull || kmax >= (1u << 19)) return ASB_OK;  // distances would not fit the tables: no pruning
+    int rc = ensure_seeds(ctx);  // also uploads the read-id indexed offset / length arrays
+    if (rc) return rc;
+    if (!ctx->seeds_ready) {  // seed_lb off: the arrays are still needed
+        CU(ctx->d_roff_all.ensure((size_t)n + 1)); CU(ctx->d_rlen_all.ensure(n));
+        CU(cudaMemcpyAsync(ctx->d_roff_all.p, ctx->h_roff.data(), sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_rlen_all.p, ctx->h_rlen.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    CU(ctx->d_cword.ensure(n)); CU(ctx->d_cl_u.ensure((size_t)n + 32)); CU(ctx->d_cl_piv.ensure(kClMaxPivots));
+    CU(cudaMemsetAsync(ctx->d_cword.p, 0xFF, sizeof(uint32_t) * n, ctx->stream));
+    std::vector<uint32_t> cword(n, kUncovered), uncovered(n), pivots;
+    for (uint32_t r = 0; r < n; ++r) uncovered[r] = r;
+    uint64_t rng = 0x9E3779B97F4A7C15ull ^ ((uint64_t)n << 20) ^ kmax;
+    auto next = [&rng]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+    const uint32_t target_left = n / 500;  // stop when 99.8 % of the reads are covered
+    for (int round = 0; round < 64 && uncovered.size() > target_left && pivots.size() < kClMaxPivots; ++round) {
+        // -- candidates: a deterministic sample of the uncovered reads
+        const uint32_t nu = (uint32_t)uncovered.size();
+        std::vector<uint32_t> cand;
+        {
+            const uint32_t want = std::min<uint32_t>({kClRound, nu, kClMaxPivots - (uint32_t)pivots.size()});
+            std::vector<uint32_t> pick;
+            for (uint32_t tries = 0; pick.size() < want && tries < 8 * want; ++tries) {
+                const uint32_t x = (uint32_t)(next() % nu);
+                if (std::find(pick.begin(), pick.end(), x) == pick.end()) pick.push_back(x);
+            }
+            std::sort(pick.begin(), pick.end());
+            for (uint32_t x : pick) cand.push_back(uncovered[x]);
+        }
+        const uint32_t nc = (uint32_t)cand.size();
+        if (nc == 0) break;
+        // -- drop candidates covered by an earlier candidate of this round (both orientations)
+        CU(ctx->d_cl_u.ensure(std::max<uint32_t>(n + 32, nc)));
+        CU(cudaMemcpyAsync(ctx->d_cl_u.p, cand.data(), sizeof(uint32_t) * nc, cudaMemcpyHostToDevice, ctx->stream));
+        uint64_t total = (uint64_t)nc * 2 * nc;
+        CU(ctx->d_cl_keys.ensure(total)); CU(ctx->d_cl_st.ensure(total)); CU(ctx->d_cl_out.ensure(total));
+        asb::asb_cl_gen_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(ctx->d_cl_u.p, nc, ctx->d_cl_u.p, nc, ctx->d_cl_keys.p, ctx->d_cl_st.p);
+        CU(cudaGetLastError());
+        rc = capped_exact_dev(ctx, ctx->d_cl_keys.p, ctx->d_cl_st.p, total, (int)kmax, ctx->d_cl_out.p, 0);
+        if (rc) return rc;
+        std::vector<int32_t> cc(total);
+        CU(cudaMemcpyAsync(cc.data(), ctx->d_cl_out.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        std::vector<uint32_t> acc_idx;  // indices into cand
+        for (uint32_t c = 0; c < nc; ++c) {
+            bool dup = false;
+            for (uint32_t a : acc_idx) dup = dup || cc[((uint64_t)a * 2 + 0) * nc + c] >= 0 || cc[((uint64_t)a * 2 + 1) * nc + c] >= 0;
+            if (!dup) acc_idx.push_back(c);
+        }
+        std::vector<uint32_t> acc;
+        for (uint32_t a : acc_idx) acc.push_back(cand[a]);
+        const uint32_t na = (uint32_t)acc.size();
+        // -- the uncovered reads against the new pivots: reads in length order, so that the 32 targets of a warp need
+        // the same window, padded to whole warps (a warp never mixes the longest reads of one pass with the shortest
+        // of the next)
+        const uint32_t base = (uint32_t)pivots.size();
+        std::vector<uint32_t> ul(uncovered);
+        std::stable_sort(ul.begin(), ul.end(), [ctx](uint32_t x, uint32_t y) { return ctx->h_rlen[x] < ctx->h_rlen[y]; });
+        const uint32_t nup = (nu + 31u) & ~31u;
+        ul.resize(nup, ul.back());
+        int need = 1;
+        for (uint32_t a : acc)
+            for (uint32_t u = 0; u < nup; u += 32)
+                need = std::max(need, slice_need((int)ctx->h_rlen[a], (int)ctx->h_rlen[ul[u]], (int)ctx->h_rlen[ul[u + 31]], (int)kmax));
+        CU(ctx->d_cl_u.ensure(std::max<uint32_t>(n + 32, nup)));
+        CU(cudaMemcpyAsync(ctx->d_cl_piv.p + base, acc.data(), sizeof(uint32_t) * na, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_cl_u.p, ul.data(), sizeof(uint32_t) * nup, cudaMemcpyHostToDevice, ctx->stream));
+        total = (uint64_t)na * 2 * nup;
+        CU(ctx->d_cl_keys.ensure(total)); CU(ctx->d_cl_st.ensure(total)); CU(ctx->d_cl_out.ensure(total));
+        asb::asb_cl_gen_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(ctx->d_cl_piv.p + base, na, ctx->d_cl_u.p, nup, ctx->d_cl_keys.p, ctx->d_cl_st.p);
+        CU(cudaGetLastError());
+        rc = capped_exact_dev(ctx, ctx->d_cl_keys.p, ctx->d_cl_st.p, total, (int)kmax, ctx->d_cl_out.p, need);
+        if (rc) return rc;
+        asb::asb_cl_assign_kernel<<<grid_for(ctx, nup, 256), 256, 0, ctx->stream>>>(ctx->d_cl_out.p, ctx->d_cl_u.p, nup, na, base, ctx->d_cword.p);
+        CU(cudaGetLastError());
+        ctx->launches += 3;
+        CU(cudaMemcpyAsync(cword.data(), ctx->d_cword.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        pivots.insert(pivots.end(), acc.begin(), acc.end());
+        std::vector<uint32_t> left;
+        for (uint32_t r : uncovered) if (cword[r] == kUncovered) left.push_back(r);
+        const size_t gained = uncovered.size() - left.size();
+        uncovered.swap(left);
+        // a round of pivots costs about 2 * na rows of the all-pairs job: it must cover a fair share of the reads
+        if (gained < (size_t)na * 4 + n / 200) break;
+    }
+    const uint32_t m = (uint32_t)pivots.size();
+    ctx->cl_kmax = kmax; ctx->cl_npiv = m; ctx->cl_covered = n - (uint32_t)uncovered.size();
+    ctx->cl_ready = true;
+    if (m == 0) return ASB_OK;
+    // -- pivot x pivot lower bounds, both relative orientations, exact up to 3 * kmax (= the largest k + a + b)
+    const uint32_t cap2 = 3 * kmax;
+    const uint64_t total = (uint64_t)m * 2 * m;
+    CU(ctx->d_cl_keys.ensure(total)); CU(ctx->d_cl_st.ensure(total)); CU(ctx->d_cl_out.ensure(total)); CU(ctx->d_pivD.ensure(total));
+    asb::asb_cl_gen_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(ctx->d_cl_piv.p, m, ctx->d_cl_piv.p, m, ctx->d_cl_keys.p, ctx->d_cl_st.p);
+    CU(cudaGetLastError());
+    rc = capped_exact_dev(ctx, ctx->d_cl_keys.p, ctx->d_cl_st.p, total, (int)cap2, ctx->d_cl_out.p, 0);
+    if (rc) return rc;
+    asb::asb_cl_matrix_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(ctx->d_cl_out.p, total, cap2, ctx->d_pivD.p);
+    CU(cudaGetLastError());
+    ctx->launches += 2;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return ASB_OK;
+}
+
+}  // namespace
+
 extern "C" {
 
 int asb_version(void) { return 100; }
@@ -846,7 +1156,7 @@ int asb_create(int device, void* stream, asb_ctx** out)
     else { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * C_COUNT);
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = ctx->d_ctr.ensure(C_COUNT);
     if (e != cudaSuccess) { asb_destroy(ctx); return ASB_E_CUDA; }
     *out = ctx;
@@ -870,7 +1180,7 @@ void asb_destroy(asb_ctx* ctx)
     ctx->d_bh_alt2.release(); ctx->d_bh_line.release(); ctx->d_bh_first.release();
     ctx->d_qbits.release(); ctx->d_seed_off.release(); ctx->d_order.release(); ctx->d_seeds_f.release(); ctx->d_seeds_r.release(); ctx->d_base2.release();
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
-    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -882,6 +1192,9 @@ int asb_set_param(asb_ctx* ctx, const char* name, double value)
     else if (!strcmp(name, "screen_frac")) { if (value <= 0 || value > 1) return fail(ctx, ASB_E_ARG, "screen_frac in (0,1]"); ctx->screen_frac = value; }
     else if (!strcmp(name, "push_thresh")) { if (value < 0 || value > 31) return fail(ctx, ASB_E_ARG, "push_thresh in [0,31]"); ctx->push_thresh = (int)value; }
     else if (!strcmp(name, "seed_lb")) { ctx->seed_lb = value != 0; }
+    else if (!strcmp(name, "prune")) { ctx->prune = value != 0; }
+    else if (!strcmp(name, "prune_min_reads")) { ctx->prune_min_reads = (uint32_t)std::max(0.0, value); ctx->cl_ready = false; }
+    else if (!strcmp(name, "prune_min_pairs")) { ctx->prune_min_pairs = (uint64_t)std::max(0.0, value); }
     else if (!strcmp(name, "cont_thresh")) { if (value < 0 || value > 32) return fail(ctx, ASB_E_ARG, "cont_thresh in [0,32]"); ctx->cont_thresh = (int)value; }
     else return fail(ctx, ASB_E_ARG, "unknown parameter %s", name);
     return ASB_OK;
@@ -893,6 +1206,7 @@ int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, u
     CU(cudaSetDevice(ctx->device));
     ctx->in_batch = false;
     ctx->text_ready = false;
+    ctx->cl_ready = false;
     const uint64_t nbytes = n_reads ? offs[n_reads] : 0;
     ctx->n_reads = n_reads;
     ctx->h_roff.assign((size_t)n_reads + 1, 0);
@@ -1007,6 +1321,7 @@ int asb_batch_begin(asb_ctx* ctx, const uint32_t* order, uint32_t n, const uint3
     ctx->next_row = 0;
     ctx->rec_n = 0;
     ctx->in_batch = true;
+    ctx->prune_mode = 0;
     return ASB_OK;
 }
 
@@ -1029,15 +1344,22 @@ static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, 
     info->fwd_survivors = nF;
     uint64_t* keys; uint32_t* vals;
     // F: full forward pass
+    float lists_ms = 0.f, ms = 0.f;
     rc = sort_list(ctx, ctx->d_F.p, nullptr, nF, &keys, nullptr); if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
     rc = run_list(ctx, B, M_FWD, cls, keys, nullptr, nF); if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[5], ctx->stream));
     rc = read_counters(ctx); if (rc) return rc;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); lists_ms += ms;
     const uint64_t nR = ctx->h_ctr[C_R];
     info->rc_survivors = nR;
     // R: full compl_reverse pass
     rc = sort_list(ctx, ctx->d_R.p, nullptr, nR, &keys, nullptr); if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
     rc = run_list(ctx, B, M_RC, cls, keys, nullptr, nR); if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[5], ctx->stream));
     rc = read_counters(ctx); if (rc) return rc;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); lists_ms += ms;
     const uint64_t nZ = ctx->h_ctr[C_Z];
     info->zone_checks = nZ;
     // Z: exact forward decision at drev
@@ -1046,9 +1368,13 @@ static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, 
         const int zbt = kClasses[zcls];
         DevBatch BZ = B;
         set_layout(ctx, BZ, peq_stride(wmax, zbt), false);
+        CU(cudaEventRecord(ctx->ev[4], ctx->stream));
         rc = run_list(ctx, BZ, M_ZONE, zcls, keys, vals, nZ); if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev[5], ctx->stream));
     }
     rc = read_counters(ctx); if (rc) return rc;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); lists_ms += ms;
+    info->lists_ms = lists_ms;
     const uint64_t nO = ctx->h_ctr[C_O];
     rc = sort_list(ctx, ctx->d_O.p, ctx->d_Ov.p, nO, &ctx->rec_keys, &ctx->rec_vals); if (rc) return rc;
     ctx->rec_n = nO;
@@ -1070,52 +1396,79 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     uint32_t r0 = ctx->next_row;
     while (r0 < n && ctx->h_hi[r0] == r0) ++r0;
     if (n == 0 || r0 >= n) { ctx->next_row = n; ctx->rec_n = 0; return ASB_DONE; }
-    // slab: rows of one window class, at most pair_cap pairs
+    // cluster pruning: worth trying on a big batch of a big read set; the first slab of the batch probes it
+    int rc;
+    if (ctx->prune_mode == 0) {
+        uint64_t tl = 0;
+        for (uint32_t p = 0; p < n; ++p) tl += ctx->h_hi[p] - p;
+        if (!ctx->prune || ctx->n_reads < ctx->prune_min_reads || tl < ctx->prune_min_pairs) ctx->prune_mode = -1;
+        else {
+            cudaEvent_t& e0 = ctx->ev[0]; cudaEvent_t& e1 = ctx->ev[3];
+            CU(cudaEventRecord(e0, ctx->stream));
+            const bool fresh = !(ctx->cl_ready && ctx->cl_kmax == ctx->h_pmax_dpass[ctx->table_len - 1]);
+            rc = ensure_clusters(ctx, ctx->h_pmax_dpass[ctx->table_len - 1]);
+            if (rc) return rc;
+            CU(cudaEventRecord(e1, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            float cms = 0;
+            CU(cudaEventElapsedTime(&cms, e0, e1));
+            ctx->cl_ms = fresh ? cms : 0.f;
+            if (!ctx->cl_ready || ctx->cl_npiv == 0 || 2ull * ctx->cl_covered < ctx->n_reads) ctx->prune_mode = -1;  // no cluster structure
+        }
+    }
+    const bool try_prune = ctx->prune_mode >= 0;
+    // slab: rows of one window class, at most pair_cap pairs (once pruning is known to work: 2^30, few pairs survive)
+    const uint64_t slab_cap = ctx->prune_mode == 1 ? std::max<uint64_t>(ctx->pair_cap, 1ull << 30) : ctx->pair_cap;
     const int cls = class_for(std::min(need_words(ctx, r0, ctx->h_pmax_dpass, 0), (int)((ctx->h_len[r0] + 31) / 32)));
     // Rows are dealt to the ranks cyclically (row p belongs to rank p % world): a rank then sees whole rows, so the
     // row-runs of its sorted lists are as long as on a single GPU (dealing 32-target groups instead left 1/world of
     // every row on each rank and the list warps mostly empty at 8 GPUs).  Neighbouring rows have almost the same
     // number of partners, so the shares differ by O(n) pairs of O(n^2 / world).
-    uint64_t pairs = 0, groups = 0, my_pairs = 0;
+    uint64_t pairs = 0, my_pairs = 0;
     uint32_t r1 = r0;
     int zneed = 0;
     uint32_t wmax = 1;
-    std::vector<uint32_t> prefix;
-    prefix.push_back(0);
+    std::vector<uint32_t> my_rows;
     while (r1 < n) {
         const uint64_t cnt = ctx->h_hi[r1] - r1;
         if (cnt) {
             const int W = (int)((ctx->h_len[r1] + 31) / 32);
             const int c2 = class_for(std::min(need_words(ctx, r1, ctx->h_pmax_dpass, 0), W));
             if (c2 != cls) break;
-            if (r1 > r0 && pairs + cnt > ctx->pair_cap * ctx->world) break;  // pair_cap is per rank
+            if (r1 > r0 && pairs + cnt > slab_cap * ctx->world) break;  // the cap is per rank
             zneed = std::max(zneed, std::min(need_words(ctx, r1, ctx->h_pmax_drev, 1), W));
             wmax = std::max<uint32_t>(wmax, (uint32_t)W);
+            if (r1 % ctx->world == ctx->rank) { my_rows.push_back(r1); my_pairs += cnt; }
         }
         pairs += cnt;
-        if (r1 % ctx->world == ctx->rank) { groups += (cnt + 31) / 32; my_pairs += cnt; }
-        if (groups > 0xFFFFFFF0ull) return fail(ctx, ASB_E_ARG, "pair_cap too large for 32-bit group indices");
-        prefix.push_back((uint32_t)groups);
         ++r1;
     }
+    // task space: blocks of kRowBlock of this rank's rows, group-major inside a block (block b holds
+    // rows x max groups task slots; a slot past the end of a shorter row is skipped by the kernel)
+    std::vector<uint32_t> prefix;
+    prefix.push_back(0);
+    uint64_t groups = 0;
+    for (size_t b = 0; b < my_rows.size(); b += kRowBlock) {
+        const size_t e = std::min(my_rows.size(), b + (size_t)kRowBlock);
+        uint64_t maxg = 0;
+        for (size_t x = b; x < e; ++x) maxg = std::max<uint64_t>(maxg, ((uint64_t)(ctx->h_hi[my_rows[x]] - my_rows[x]) + 31) / 32);
+        groups += maxg * (e - b);
+        if (groups > 0xFFFFFFF0ull) return fail(ctx, ASB_E_ARG, "pair_cap too large for 32-bit task indices");
+        prefix.push_back((uint32_t)groups);
+    }
     const int zcls = class_for(zneed);
-    int rc = ensure_seeds(ctx);
+    rc = ensure_seeds(ctx);
     if (rc) return rc;
-    const uint64_t cap = std::max<uint64_t>(my_pairs, 32);
-    rc = ensure_lists(ctx, cap);
-    if (rc) return rc;
-    CU(ctx->d_grp.ensure(prefix.size()));
+    CU(ctx->d_grp.ensure(prefix.size())); CU(ctx->d_myrows.ensure(std::max<size_t>(my_rows.size(), 1)));
     CU(cudaMemcpyAsync(ctx->d_grp.p, prefix.data(), sizeof(uint32_t) * prefix.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
-
+    if (!my_rows.empty()) CU(cudaMemcpyAsync(ctx->d_myrows.p, my_rows.data(), sizeof(uint32_t) * my_rows.size(), cudaMemcpyHostToDevice, ctx->stream));
     DevBatch B;
     memset(&B, 0, sizeof B);
     B.codes_f = ctx->d_cf.p; B.codes_r = ctx->d_cr.p; B.pos_off = ctx->d_pos_off.p; B.pos_len = ctx->d_pos_len.p; B.hi = ctx->d_hi.p;
     B.dpass = ctx->d_dpass.p; B.drev = ctx->d_drev.p; B.table_len = ctx->table_len; B.n = n; B.sigma = ctx->sigma;
-    B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
-    B.ctr = ctx->d_ctr.p; B.list_cap = ctx->list_cap;
-    B.grp_prefix = ctx->d_grp.p; B.row_begin = r0; B.rows = r1 - r0;
-    B.rank = 0; B.world = 1;  // grp_prefix already holds this rank's rows only
+    B.ctr = ctx->d_ctr.p;
+    B.blk_prefix = ctx->d_grp.p; B.my_rows = ctx->d_myrows.p;
+    B.n_my = (uint32_t)my_rows.size(); B.n_blocks = (uint32_t)prefix.size() - 1;
     B.n_tasks = (uint32_t)groups;
     B.screen_cols_num = std::max(1, (int)(ctx->screen_frac * 256.0 + 0.5));
     B.push_thresh = ctx->push_thresh;
@@ -1123,18 +1476,51 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     const int bt = kClasses[cls];
     set_layout(ctx, B, peq_stride((int)wmax, bt), true);
     B.pos_read = ctx->d_order.p;
+    B.cword = ctx->d_cword.p; B.pivD = ctx->d_pivD.p; B.n_piv = ctx->cl_npiv;
+    const int pgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 8, std::max<uint64_t>(((uint64_t)B.n_tasks + 7) / 8, 1));
 
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if (B.n_tasks) {
-        screen_fn fn = Fns::screen(cls);
-        LaunchShape ls;
-        rc = launch_cfg(ctx, fn, B, &ls);
-        if (rc) return rc;
-        const uint64_t blocks = ((uint64_t)B.n_tasks + ls.warps - 1) / ls.warps;
-        const int grid = (int)std::min<uint64_t>((uint64_t)ls.grid, std::max<uint64_t>(blocks, 1));
-        fn<<<grid, ls.warps * 32, ls.smem, ctx->stream>>>(B);
+    bool pruned = false;
+    if (try_prune && B.n_tasks) {
+        // count pass: how many pairs does the bound leave for the exact passes?
+        CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
+        asb_prune<<<pgrid, 256, 0, ctx->stream>>>(B, 1);
         CU(cudaGetLastError());
         ctx->launches++;
+        rc = read_counters(ctx);
+        if (rc) return rc;
+        const uint64_t left = ctx->h_ctr[C_F] + ctx->h_ctr[C_R];
+        if (ctx->prune_mode == 0) ctx->prune_mode = 2 * left <= my_pairs ? 1 : -1;  // the probe slab decides for the batch
+        if (ctx->prune_mode == 1) {
+            rc = ensure_lists(ctx, left + 32);
+            if (rc) return rc;
+            B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
+            B.list_cap = ctx->list_cap;
+            CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
+            asb_prune<<<pgrid, 256, 0, ctx->stream>>>(B, 0);
+            CU(cudaGetLastError());
+            ctx->launches++;
+            pruned = true;
+            info->pruned_pairs = my_pairs - left;
+        }
+    }
+    if (!pruned) {
+        rc = ensure_lists(ctx, std::max<uint64_t>(my_pairs, 32));
+        if (rc) return rc;
+        B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
+        B.list_cap = ctx->list_cap;
+        CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
+        if (B.n_tasks) {
+            screen_fn fn = Fns::screen(cls);
+            LaunchShape ls;
+            rc = launch_cfg(ctx, fn, B, &ls);
+            if (rc) return rc;
+            const uint64_t blocks = ((uint64_t)B.n_tasks + ls.warps - 1) / ls.warps;
+            const int grid = (int)std::min<uint64_t>((uint64_t)ls.grid, std::max<uint64_t>(blocks, 1));
+            fn<<<grid, ls.warps * 32, ls.smem, ctx->stream>>>(B);
+            CU(cudaGetLastError());
+            ctx->launches++;
+        }
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     rc = read_counters(ctx);
@@ -1151,6 +1537,8 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     info->pairs = my_pairs;
     info->row_begin = r0; info->row_end = r1;
     info->launches = ctx->launches;
+    info->cluster_ms = ctx->cl_ms; ctx->cl_ms = 0.f;  // charged to the step that built the clusters
+    info->n_pivots = pruned ? ctx->cl_npiv : 0;
     ctx->next_row = r1;
     return ASB_OK;
 }

@@ -157,16 +157,6 @@ __global__ void __launch_bounds__(256) asb_uf_label_kernel(uint32_t* parent, uin
 
 }  // namespace asb
 
-namespace {
-
-unsigned grid_for(const asb_ctx* ctx, uint64_t n, int block)
-{
-    const uint64_t blocks = (n + block - 1) / block;
-    return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(blocks, (uint64_t)ctx->sm_count * 16));
-}
-
-}  // namespace
-
 extern "C" {
 
 int asb_lines_upload(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const uint32_t* milli, uint64_t n)

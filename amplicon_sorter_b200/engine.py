@@ -33,7 +33,7 @@ class _Slot:
 
 
 TOTALS = ("pairs", "n_records", "fwd_survivors", "rc_survivors", "zone_checks", "word_updates", "screen_word_updates",
-          "useful_word_updates", "screen_useful_word_updates", "screen_ms", "total_ms", "launches")
+          "useful_word_updates", "screen_useful_word_updates", "screen_ms", "total_ms", "launches", "pruned_pairs", "cluster_ms", "lists_ms")
 
 
 class EngineBase:
@@ -163,8 +163,8 @@ class Engine(EngineBase):
         """All steps of one batch.  Returns (records sorted by (i_pos, j_pos), totals dict)."""
         self.batch_begin(order, hi, dpass, drev, rank, world)
         recs = []
-        tot = {"pairs": 0, "n_records": 0, "fwd_survivors": 0, "rc_survivors": 0, "zone_checks": 0,
-               "word_updates": 0, "screen_word_updates": 0, "screen_ms": 0.0, "total_ms": 0.0, "steps": 0}
+        tot = dict.fromkeys(TOTALS, 0)
+        tot["steps"] = 0
         while True:
             info = self.batch_step()
             if info is None:

@@ -281,6 +281,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--pair-cap", type=float, default=0)
+    ap.add_argument("--prune", type=int, default=1, choices=[0, 1], help="0 = switch the pivot bound off (every pair goes through the screen kernel)")
     ap.add_argument("--tmpdir", default=None, help="where the e2e arm writes <stem>_compare.tmp (default: a fresh temp dir)")
     a = ap.parse_args()
     if a.reads:
@@ -316,6 +317,7 @@ def main():
     parity = {} if a.no_parity else parity_check(facade, world)
     if a.pair_cap:
         facade.set_param("pair_cap", a.pair_cap)
+    facade.set_param("prune", a.prune)
 
     # ---- resident-input arm -------------------------------------------------------------------
     codes_bytes = 2 * int(w["buf"].nbytes)  # forward + compl_reverse symbol codes
@@ -384,31 +386,48 @@ def main():
         parity["records_crc"] = crc
 
     lop3, mix = eng.int_peak(4000)
-    screen_s = agg["screen_ms"] / 1e3 / world  # rank-sum of device times -> mean per rank
-    total_s = agg["total_ms"] / 1e3 / world
-    wu_rate = agg["screen_word_updates"] / max(screen_s, 1e-9) / world  # per GPU
-    achieved = wu_rate * ALU_OPS_PER_WORD_UPDATE / 1e12
-    useful = agg["screen_useful_word_updates"] / max(agg["screen_word_updates"], 1)
     peak = max(lop3, mix)
+    screen_s = agg["screen_ms"] / 1e3 / world  # rank-sums of device times -> mean per rank
+    lists_s = agg["lists_ms"] / 1e3 / world
+    total_s = agg["total_ms"] / 1e3 / world
+    pruned_frac = agg["pruned_pairs"] / max(agg["pairs"], 1)
     traffic = _ncu_traffic(a.config)
+    # the dominant kernel: asb_screen when every pair goes through the banded pass; asb_lists (the exact passes on
+    # the pairs the pivot bound leaves undecided) when most pairs are decided by asb_prune
+    if pruned_frac > 0.5 or lists_s > screen_s:
+        kern, k_s = "asb_lists", lists_s
+        k_wu, k_useful = agg["word_updates"] - agg["screen_word_updates"], agg["useful_word_updates"] - agg["screen_useful_word_updates"]
+        k_launches = 3 * agg["steps"]
+    else:
+        kern, k_s = "asb_screen", screen_s
+        k_wu, k_useful = agg["screen_word_updates"], agg["screen_useful_word_updates"]
+        k_launches = agg["steps"]
+    wu_rate = k_wu / max(k_s, 1e-9) / world  # per GPU
+    achieved = wu_rate * ALU_OPS_PER_WORD_UPDATE / 1e12
+    useful = k_useful / max(k_wu, 1)
     roofline = {"bound": "int_alu", "achieved": achieved, "peak": peak, "unit": "Tops/s (INT32 ALU-pipe lane-ops, per GPU)",
                 "frac": achieved / peak if peak else None,
                 "achieved_useful": achieved * useful, "frac_useful": achieved * useful / peak if peak else None,
                 "live_lane_fraction": useful,
-                "traffic": traffic["bytes_per_launch"] if traffic else None, "traffic_source": traffic["source"] if traffic else None,
-                "kernel": "asb_screen", "launches": agg["steps"],
-                "avg_launch_ms": agg["screen_ms"] / max(agg["steps"], 1) / world,
-                "kernel_share_of_step": screen_s / max(t_res, 1e-9),
-                "kernel_share_of_device_time": screen_s / max(total_s, 1e-9),
+                "traffic": traffic["bytes_per_launch"] if traffic and traffic.get("kernel") == kern else None,
+                "traffic_source": traffic["source"] if traffic and traffic.get("kernel") == kern else None,
+                "kernel": kern, "launches": k_launches,
+                "avg_launch_ms": k_s * 1e3 * world / max(k_launches, 1) / world,
+                "kernel_share_of_step": k_s / max(t_res, 1e-9),
+                "kernel_share_of_device_time": k_s / max(total_s, 1e-9),
+                "device_time_ms_per_step": {"asb_screen or asb_prune": screen_s * 1e3 / a.steps, "asb_lists": lists_s * 1e3 / a.steps,
+                                            "all kernels of the steps (events)": total_s * 1e3 / a.steps,
+                                            "pivot selection + read assignment (first step of a job)": agg["cluster_ms"] / world / a.steps},
                 "word_updates_per_s": wu_rate, "alu_ops_per_word_update": ALU_OPS_PER_WORD_UPDATE,
                 "word_updates_per_pair": agg["word_updates"] / max(agg["pairs"], 1),
                 "useful_word_updates_per_pair": agg["useful_word_updates"] / max(agg["pairs"], 1),
-                "note": "achieved counts EXECUTED lane-slots (32 lanes x active words x columns of every warp); achieved_useful only the "
-                        "words each lane itself still needed (live_lane_fraction = useful / executed, counted by the kernel)",
+                "pairs_decided_by_pivot_bound": pruned_frac,
+                "note": "achieved counts EXECUTED lane-slots (32 lanes x active words x columns of every warp) of the dominant kernel; "
+                        "achieved_useful only the words each lane itself still needed (live_lane_fraction = useful / executed, counted by the kernel)",
                 "peak_source": "asb_int_peak measured live on this GPU: best of LOP3-chain probe (%.2f) and LOP3/SHF/IADD3/LEA mix probe (%.2f); nominal 148 SM x 64 lanes x 1.965 GHz = 18.61" % (lop3, mix),
                 "nominal": {"ops_per_job": nominal_ops(w), "note": "SURVEY 8(d): 20*ceil(m/32)*n*2 per pair (full-matrix Myers, both strands)",
                             "equivalent_tops": nominal_ops(w) * a.steps / t_res / 1e12 / max(world, 1)},
-                "hbm": {"peak_gbs": _measured_peak("hbm_gbs"), "note": "path is not HBM-bound: ~200 MB of symbol codes stay L2-resident"}}
+                "hbm": {"peak_gbs": _measured_peak("hbm_gbs"), "note": "path is not HBM-bound"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": t_res / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",

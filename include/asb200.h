@@ -60,6 +60,14 @@ typedef struct {
      * lane itself still needed (see band_pass): the ratio is the live-lane occupancy of the executed work. */
     uint64_t useful_word_updates;
     uint64_t screen_useful_word_updates;
+    /* Cluster pruning (parameter "prune", default on): pairs of this step that the admissible pivot bound decided
+     * on BOTH strands without an alignment (0 when the step ran the screen kernel instead); screen_ms is then the
+     * time of the pruning kernels.  cluster_ms = time spent choosing pivots and assigning reads (first step only). */
+    uint64_t pruned_pairs;
+    float cluster_ms;
+    uint32_t n_pivots;
+    float lists_ms;          /* device time of the step's three asb_lists launches (F, R, Z passes) */
+    uint32_t reserved2;
 } asb_step_info;
 
 /* Replaces nothing in the reference (it has no device): create/destroy an engine on `device`.
@@ -68,7 +76,9 @@ int asb_create(int device, void *stream, asb_ctx **out);
 void asb_destroy(asb_ctx *ctx);
 const char *asb_last_error(const asb_ctx *ctx);
 /* Tuning knobs (results never depend on them): "pair_cap", "screen_frac", "push_thresh", "cont_thresh",
- * "seed_lb" (1/0: use the admissible q-mer seed lower bound to end hopeless alignments early). */
+ * "seed_lb" (1/0: use the admissible q-mer seed lower bound to end hopeless alignments early),
+ * "prune" (1/0: decide pairs of unrelated read clusters by the triangle inequality over pivot reads; tried on jobs
+ * of at least "prune_min_reads" reads and "prune_min_pairs" pairs). */
 int asb_set_param(asb_ctx *ctx, const char *name, double value);
 
 /* Replaces the per-record `str(record.seq).upper()` payload (:551) + per-pair compl_reverse (:795):

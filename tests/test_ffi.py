@@ -21,7 +21,7 @@ def test_library_builds_and_exports_header_symbols():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_ffi.StepInfo) == 6 * 8 + 6 * 4 + 3 * 8
+    assert C.sizeof(_ffi.StepInfo) == 6 * 8 + 6 * 4 + 3 * 8 + 8 + 4 * 4
     assert _ffi.RECORD.itemsize == 16
 
 

@@ -294,3 +294,72 @@ def test_seed_bound_adversarial_edges(engine):
         got, _ = util.gpu_batch(engine, reads, sg, seed_lb=1)
         util.assert_same_records(got, want)
         assert len(want) > 8 and k - 1 in want["d"].tolist() and k in want["d"].tolist()
+
+
+def _force_prune(engine, on=True):
+    engine.set_param("prune", 1 if on else 0)
+    engine.set_param("prune_min_reads", 0 if on else 1024)
+    engine.set_param("prune_min_pairs", 0 if on else float(1 << 22))
+
+
+@pytest.mark.parametrize("cfg,scale", [(5, 0.02), (4, 0.03), (2, 0.08), (3, 0.1), (1, 1.0)])
+def test_cluster_pruning_is_only_an_optimisation(engine, cfg, scale):
+    """The pivot bound (asb_prune) decides pairs without aligning them; records must not depend on it.  Forced on
+    for these small inputs; cfg5 / cfg4 have unrelated amplicons (most pairs pruned), cfg2 / cfg3 / cfg1 are one
+    family per length window (nothing to prune: the probe slab must hand the batch back to the screen kernel)."""
+    reads, _, _ = synth.make_config(cfg, scale=scale)
+    want, st = util.oracle_batch(reads)
+    try:
+        _force_prune(engine, True)
+        got, tot = util.gpu_batch(engine, reads, pair_cap=1 << 16)
+        assert tot["pairs"] == st["pairs"]
+        util.assert_same_records(got, want)
+        if cfg in (5, 4):
+            assert tot["pruned_pairs"] > 0.5 * tot["pairs"], tot
+        parts = util.gpu_batch(engine, reads, world=3, pair_cap=1 << 16)[0]
+        util.assert_same_records(parts, want)
+        _force_prune(engine, False)
+        engine.set_param("prune", 0)
+        off, tot0 = util.gpu_batch(engine, reads, pair_cap=1 << 16)
+        util.assert_same_records(off, want)
+        assert tot0["pruned_pairs"] == 0
+    finally:
+        _force_prune(engine, False)
+        engine.set_param("prune", 1)
+        engine.set_param("pair_cap", float(1 << 26))
+
+
+def test_cluster_pruning_adversarial_boundaries(engine):
+    """Pairs that sit right on the cut-off across cluster boundaries: families whose centres are 1.0-1.6 x dpass apart
+    (the bound D - a - b is close to k), reads on both strands, reverse-complement palindromes (a read that is its own
+    compl_reverse has BOTH orientations close to its pivot) and a low-complexity family."""
+    rng = np.random.default_rng(99)
+    al = np.frombuffer(b"ACGT", dtype=np.uint8)
+    L = 400
+    base = rng.integers(0, 4, L, dtype=np.uint8)
+    centres = [base]
+    for frac in (0.05, 0.10, 0.16, 0.20, 0.24, 0.30):
+        centres.append(synth.diverge(rng, base, frac))
+    half = rng.integers(0, 4, L // 2, dtype=np.uint8)
+    centres.append(np.concatenate([half, synth.revcomp_codes(half)]))          # palindrome: equal to its compl_reverse
+    centres.append(np.tile(np.array([0, 3], dtype=np.uint8), L // 2))           # ATAT...: low complexity, self-complementary
+    centres += [rng.integers(0, 4, L, dtype=np.uint8) for _ in range(6)]       # unrelated
+    reads = []
+    for c in centres:
+        for _ in range(40):
+            r = synth.mutate(rng, c, sub=0.02, ins=0.01, dele=0.01)
+            if rng.random() < 0.5:
+                r = synth.revcomp_codes(r)
+            reads.append(al[r].tobytes())
+    want, st = util.oracle_batch(reads)
+    try:
+        _force_prune(engine, True)
+        for sg in (80.0, 90.0):
+            w, _ = util.oracle_batch(reads, sg)
+            got, tot = util.gpu_batch(engine, reads, sg, pair_cap=1 << 14)
+            util.assert_same_records(got, w)
+            assert tot["pruned_pairs"] > 0
+    finally:
+        _force_prune(engine, False)
+        engine.set_param("pair_cap", float(1 << 26))
+    assert (want["reverse"] == 1).any() and st["records"] > 1000
