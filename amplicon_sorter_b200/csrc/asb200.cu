@@ -35,7 +35,7 @@ namespace asb {
 // --------------------------------------------------------------------------------------------
 // device-side views
 // --------------------------------------------------------------------------------------------
-enum Counter : int { C_TASK = 0, C_F, C_R, C_Z, C_O, C_WORDS, C_ERR, C_USEFUL, C_COUNT };
+enum Counter : int { C_TASK = 0, C_F, C_R, C_Z, C_O, C_WORDS, C_ERR, C_USEFUL, C_OVF, C_COUNT };
 enum Mode : int { M_SCREEN = 0, M_FWD = 1, M_RC = 2, M_ZONE = 3, M_EXACT = 4 };
 enum DevErr : unsigned long long { E_BAND = 1ull, E_TABLE = 2ull, E_LIST = 4ull };
 constexpr int kRowBlock = 64;  // rows per block of the screen's task order (see DevBatch::my_rows)
@@ -72,6 +72,7 @@ struct DevBatch {
     // cluster pruning (see ensure_clusters): per READ a word (pivot, orientation, distance to it) and a matrix of lower
     // bounds of the pivot x pivot distances in both relative orientations
     const uint32_t* cword; const uint16_t* pivD; uint32_t n_piv;
+    const uint32_t* pos_cw; const uint32_t* pos_k;  // per sorted position: cluster word of its read, dpass[its length]
     // seed lower bound (K2 put to work, see myers_band.cuh::SeedLB): per-read q-mer presence bitsets and the
     // seed codes of both strands, 8 per uint4 chunk, chunks of read r from seed_off[r]
     const uint32_t* qbits; const uint4* seeds_f; const uint4* seeds_r; const uint32_t* seed_off;
@@ -375,58 +376,69 @@ __device__ __forceinline__ uint32_t cw_pivot(uint32_t w) { return w >> 20; }    
 __device__ __forceinline__ uint32_t cw_orient(uint32_t w) { return (w >> 19) & 1u; }  // 1 bit
 __device__ __forceinline__ uint32_t cw_dist(uint32_t w) { return w & 0x7FFFFu; }      // 19 bits
 
-__global__ void __launch_bounds__(256) asb_prune(const DevBatch B, const int count_only)
+// per sorted position: the cluster word of its read and the pass cut-off of its length (what a pair needs of its
+// LONGER read), so that asb_prune reads two coalesced words per pair instead of chasing order -> read -> tables
+__global__ void __launch_bounds__(256) asb_pos_tables_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ pos_len, uint32_t n,
+                                                           const uint32_t* __restrict__ cword, const uint32_t* __restrict__ dpass, uint32_t table_len,
+                                                           uint32_t* __restrict__ pos_cw, uint32_t* __restrict__ pos_k)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        pos_cw[p] = cword[order[p]];
+        const uint32_t L = pos_len[p];
+        pos_k[p] = L < table_len ? dpass[L] : 0xFFFFFFFFu;  // 0xFFFFFFFF = no distance passes
+    }
+}
+
+constexpr int kPruneChunk = 16;  // tasks per grab of the shared counter (one atomic per 512 pairs)
+
+// Appends past a list's capacity are dropped and only counted (C_F / C_R keep counting): the host then retries the
+// slab with lists of the size the counters ask for.
+__global__ void __launch_bounds__(256) asb_prune(const DevBatch B)
 {
     const int lane = threadIdx.x & 31;
-    unsigned long long nf = 0, nr = 0;
     for (;;) {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(&B.ctr[C_TASK], 1ull);
-        t = __shfl_sync(0xFFFFFFFFu, t, 0);
-        if (t >= B.n_tasks) break;
+        unsigned long long t0 = 0;
+        if (lane == 0) t0 = atomicAdd(&B.ctr[C_TASK], (unsigned long long)kPruneChunk);
+        t0 = __shfl_sync(0xFFFFFFFFu, t0, 0);
+        if (t0 >= B.n_tasks) break;
+        const uint32_t t1 = (uint32_t)min((unsigned long long)B.n_tasks, t0 + kPruneChunk);
+        // block of the first task; later tasks of the chunk walk forward
         uint32_t lo = 0, hi = B.n_blocks;
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(&B.blk_prefix[mid]) <= (uint32_t)t) lo = mid; else hi = mid;
+            if (__ldg(&B.blk_prefix[mid]) <= (uint32_t)t0) lo = mid; else hi = mid;
         }
-        const uint32_t local = (uint32_t)t - __ldg(&B.blk_prefix[lo]);
-        const uint32_t r0 = lo * kRowBlock, nrw = min((uint32_t)kRowBlock, B.n_my - r0);
-        const uint32_t gi = local / nrw;
-        const uint32_t row = __ldg(&B.my_rows[r0 + local % nrw]);
-        const uint32_t j = row + 1 + gi * 32 + lane;
-        bool needF = false, needR = false, pr = false;
-        if (j <= __ldg(&B.hi[row])) {
-            const int m = (int)__ldg(&B.pos_len[row]), n = (int)__ldg(&B.pos_len[j]);
-            const int L = n > m ? n : m;
-            int k = -1;
-            if ((uint32_t)L >= B.table_len) atomicOr(&B.ctr[C_ERR], (unsigned long long)E_TABLE);
-            else { const uint32_t kk = __ldg(&B.dpass[L]); k = kk == 0xFFFFFFFFu ? -1 : (int)kk; }
-            if (abs(n - m) <= k) {  // otherwise d >= |n - m| > k on both strands: nothing can be emitted
-                const uint32_t wa = __ldg(&B.cword[B.pos_read ? __ldg(&B.pos_read[row]) : row]);
-                const uint32_t wb = __ldg(&B.cword[B.pos_read ? __ldg(&B.pos_read[j]) : j]);
-                bool pf = false;
-                if (wa != kUncovered && wb != kUncovered) {
-                    const uint32_t x = cw_orient(wa) ^ cw_orient(wb);
-                    const uint16_t* d = B.pivD + ((size_t)cw_pivot(wa) * B.n_piv + cw_pivot(wb)) * 2;
-                    const int s = k + (int)cw_dist(wa) + (int)cw_dist(wb);
-                    pf = (int)__ldg(d + x) > s;
-                    pr = (int)__ldg(d + (x ^ 1u)) > s;
+        for (uint32_t t = (uint32_t)t0; t < t1; ++t) {
+            while (lo + 1 < B.n_blocks && __ldg(&B.blk_prefix[lo + 1]) <= t) ++lo;
+            const uint32_t local = t - __ldg(&B.blk_prefix[lo]);
+            const uint32_t r0 = lo * kRowBlock, nrw = min((uint32_t)kRowBlock, B.n_my - r0);
+            const uint32_t gi = local / nrw;
+            const uint32_t row = __ldg(&B.my_rows[r0 + local % nrw]);
+            const uint32_t j = row + 1 + gi * 32 + lane;
+            bool needF = false, needR = false, pr = false;
+            if (j <= __ldg(&B.hi[row])) {
+                const int m = (int)__ldg(&B.pos_len[row]), n = (int)__ldg(&B.pos_len[j]);  // n >= m: j follows row in the length order
+                const uint32_t kk = __ldg(&B.pos_k[j]);
+                const int k = kk == 0xFFFFFFFFu ? -1 : (int)kk;
+                if (n - m <= k) {  // otherwise d >= n - m > k on both strands: nothing can be emitted
+                    const uint32_t wa = __ldg(&B.pos_cw[row]), wb = __ldg(&B.pos_cw[j]);
+                    bool pf = false;
+                    if (wa != kUncovered && wb != kUncovered) {
+                        const uint32_t x = cw_orient(wa) ^ cw_orient(wb);
+                        const uint16_t* d = B.pivD + (size_t)cw_pivot(wa) * 2 * B.n_piv + cw_pivot(wb);  // D[P][x][Q]
+                        const int s = k + (int)cw_dist(wa) + (int)cw_dist(wb);
+                        pf = (int)__ldg(d + x * B.n_piv) > s;
+                        pr = (int)__ldg(d + (x ^ 1u) * B.n_piv) > s;
+                    }
+                    needF = !pf;
+                    needR = pf && !pr;
                 }
-                needF = !pf;
-                needR = pf && !pr;
             }
-        }
-        if (count_only) { nf += needF; nr += needR; }
-        else {  // all 32 lanes take part in the warp-aggregated appends
+            // all 32 lanes take part in the warp-aggregated appends
             const uint64_t key = ((uint64_t)row << 32) | j;
-            warp_push(needF, B.F, nullptr, &B.ctr[C_F], B.list_cap, key | (pr ? 0x80000000ull : 0ull), 0u, &B.ctr[C_ERR]);
-            warp_push(needR, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]);
+            warp_push(needF, B.F, nullptr, &B.ctr[C_F], B.list_cap, key | (pr ? 0x80000000ull : 0ull), 0u, &B.ctr[C_OVF]);
+            warp_push(needR, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_OVF]);
         }
-    }
-    if (count_only) {
-        nf = warp_sum_u64(nf); nr = warp_sum_u64(nr);
-        if (lane == 0 && nf) atomicAdd(&B.ctr[C_F], nf);
-        if (lane == 0 && nr) atomicAdd(&B.ctr[C_R], nr);
     }
 }
 
@@ -746,6 +758,7 @@ struct asb_ctx {
     uint32_t prune_min_reads = 1024; uint64_t prune_min_pairs = 1ull << 22;  // below these a job is a few milliseconds anyway
     bool cl_ready = false; uint32_t cl_kmax = 0, cl_npiv = 0, cl_covered = 0;
     int prune_mode = 0;         // this batch: 0 = undecided, 1 = prune path, -1 = screen path
+    DevBuf<uint32_t> d_pos_cw, d_pos_k; bool pos_tables_ready = false; double prune_left_ratio = 0.0;
     float cl_ms = 0.f;          // device + host time spent building the clusters (reported with the first step)
 };
 
@@ -1322,6 +1335,8 @@ int asb_batch_begin(asb_ctx* ctx, const uint32_t* order, uint32_t n, const uint3
     ctx->rec_n = 0;
     ctx->in_batch = true;
     ctx->prune_mode = 0;
+    ctx->pos_tables_ready = false;
+    ctx->prune_left_ratio = 0.0;
     return ASB_OK;
 }
 
@@ -1477,29 +1492,45 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     set_layout(ctx, B, peq_stride((int)wmax, bt), true);
     B.pos_read = ctx->d_order.p;
     B.cword = ctx->d_cword.p; B.pivD = ctx->d_pivD.p; B.n_piv = ctx->cl_npiv;
-    const int pgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 8, std::max<uint64_t>(((uint64_t)B.n_tasks + 7) / 8, 1));
+    const int pgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 8, std::max<uint64_t>(((uint64_t)B.n_tasks + 8 * kPruneChunk - 1) / (8 * kPruneChunk), 1));
 
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     bool pruned = false;
     if (try_prune && B.n_tasks) {
-        // count pass: how many pairs does the bound leave for the exact passes?
-        CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
-        asb_prune<<<pgrid, 256, 0, ctx->stream>>>(B, 1);
-        CU(cudaGetLastError());
-        ctx->launches++;
-        rc = read_counters(ctx);
-        if (rc) return rc;
-        const uint64_t left = ctx->h_ctr[C_F] + ctx->h_ctr[C_R];
-        if (ctx->prune_mode == 0) ctx->prune_mode = 2 * left <= my_pairs ? 1 : -1;  // the probe slab decides for the batch
-        if (ctx->prune_mode == 1) {
-            rc = ensure_lists(ctx, left + 32);
+        if (!ctx->pos_tables_ready) {
+            CU(ctx->d_pos_cw.ensure(n)); CU(ctx->d_pos_k.ensure(n));
+            asb_pos_tables_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->d_order.p, ctx->d_pos_len.p, n, ctx->d_cword.p, ctx->d_dpass.p,
+                                                                                  ctx->table_len, ctx->d_pos_cw.p, ctx->d_pos_k.p);
+            CU(cudaGetLastError());
+            ctx->launches++;
+            ctx->pos_tables_ready = true;
+        }
+        B.pos_cw = ctx->d_pos_cw.p; B.pos_k = ctx->d_pos_k.p;
+        // One pass appends the pairs the bound leaves for the exact passes.  The probe slab has screen-sized lists
+        // (it may still fall back to the screen kernel); later slabs size their lists from the share that survived
+        // so far and run again in the rare case that the estimate was too small.
+        uint64_t lcap = ctx->prune_mode == 0 ? std::max<uint64_t>(my_pairs, 32)
+                                             : std::max<uint64_t>(1ull << 20, (uint64_t)((double)my_pairs * ctx->prune_left_ratio * 1.5) + 4096);
+        uint64_t left = 0;
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            rc = ensure_lists(ctx, std::min<uint64_t>(lcap, std::max<uint64_t>(my_pairs, 32)));
             if (rc) return rc;
             B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
             B.list_cap = ctx->list_cap;
             CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
-            asb_prune<<<pgrid, 256, 0, ctx->stream>>>(B, 0);
+            asb_prune<<<pgrid, 256, 0, ctx->stream>>>(B);
             CU(cudaGetLastError());
             ctx->launches++;
+            rc = read_counters(ctx);
+            if (rc) return rc;
+            left = ctx->h_ctr[C_F] + ctx->h_ctr[C_R];
+            if (left + 32 <= ctx->list_cap) break;  // room for everything the later passes can append
+            if (attempt == 2) return fail(ctx, ASB_E_INTERNAL, "pruning lists overflowed twice");
+            lcap = left + 32;
+        }
+        ctx->prune_left_ratio = std::max(ctx->prune_left_ratio, (double)left / (double)std::max<uint64_t>(my_pairs, 1));
+        if (ctx->prune_mode == 0) ctx->prune_mode = 2 * left <= my_pairs ? 1 : -1;  // the probe slab decides for the batch
+        if (ctx->prune_mode == 1) {
             pruned = true;
             info->pruned_pairs = my_pairs - left;
         }
@@ -1795,7 +1826,7 @@ int asb_distance_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const
     DevBatch B;
     memset(&B, 0, sizeof B);
     B.codes_f = ctx->d_cf.p; B.codes_r = ctx->d_cr.p; B.pos_off = ctx->d_pos_off.p; B.pos_len = ctx->d_pos_len.p;
-    B.n = n; B.sigma = ctx->sigma; B.ctr = ctx->d_ctr.p; B.ex_strand = d_st.p; B.ex_out = d_out.p; B.ex_hw = mode;
+    B.n = n; B.sigma = ctx->sigma; B.ctr = ctx->d_ctr.p; B.ex_strand = d_st.p; B.ex_out = d_out.p; B.ex_hw = mode; B.ex_cap = -1;
     set_layout(ctx, B, peq_stride((int)wmax, 0), false);
     int rc = run_list(ctx, B, M_EXACT, kNumClasses - 1, d_keys.p, nullptr, npairs);
     if (rc) return rc;

@@ -188,36 +188,45 @@ int asb_text_begin(asb_ctx* ctx, const uint32_t* idx_sorted, uint32_t n_pos, con
     return ASB_OK;
 }
 
-int asb_text_step(asb_ctx* ctx, const asb_record* dev_recs, uint64_t n, int sort, char* host_dst, uint64_t cap, uint64_t* nbytes)
+int asb_text_load(asb_ctx* ctx, const asb_record* dev_recs, uint64_t n, int sort)
+{
+    if (!ctx || (n && !dev_recs)) return fail(ctx, ASB_E_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->rec_n = 0;
+    if (n == 0) return ASB_OK;
+    CU(ctx->d_t_keys.ensure(n)); CU(ctx->d_t_vals.ensure(n));
+    asb::asb_text_unpack_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(dev_recs, n, ctx->d_t_keys.p, ctx->d_t_vals.p);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    ctx->rec_keys = ctx->d_t_keys.p; ctx->rec_vals = ctx->d_t_vals.p;
+    if (sort && n > 1) {  // per-rank lists are sorted; their union (rows dealt cyclically) is not
+        CU(ctx->d_t_keys_alt.ensure(n)); CU(ctx->d_t_vals_alt.ensure(n));
+        cub::DoubleBuffer<uint64_t> kb(ctx->d_t_keys.p, ctx->d_t_keys_alt.p);
+        cub::DoubleBuffer<uint32_t> vb(ctx->d_t_vals.p, ctx->d_t_vals_alt.p);
+        const int end_bit = std::min(64, 32 + bits_for(ctx->n));
+        size_t tmp = 0;
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
+        CU(ctx->d_tmp.ensure(tmp));
+        CU(cub::DeviceRadixSort::SortPairs(ctx->d_tmp.p, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
+        ctx->rec_keys = kb.Current(); ctx->rec_vals = vb.Current();
+    }
+    CU(cudaStreamSynchronize(ctx->stream));  // dev_recs may be released by the caller
+    ctx->rec_n = n;
+    return ASB_OK;
+}
+
+int asb_text_step(asb_ctx* ctx, uint64_t first, uint64_t count, char* host_dst, uint64_t cap, uint64_t* nbytes)
 {
     if (!ctx || !nbytes) return fail(ctx, ASB_E_ARG, "null argument");
     *nbytes = 0;
     if (!ctx->text_ready) return fail(ctx, ASB_E_ARG, "asb_text_step without asb_text_begin");
+    if (first > ctx->rec_n || count > ctx->rec_n - first) return fail(ctx, ASB_E_ARG, "records [%llu, +%llu) are outside the current %llu records",
+                                                                      (unsigned long long)first, (unsigned long long)count, (unsigned long long)ctx->rec_n);
     CU(cudaSetDevice(ctx->device));
-    const uint64_t* keys; const uint32_t* vals;
-    if (dev_recs) {
-        if (n == 0) return ASB_OK;
-        CU(ctx->d_t_keys.ensure(n)); CU(ctx->d_t_vals.ensure(n));
-        asb::asb_text_unpack_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(dev_recs, n, ctx->d_t_keys.p, ctx->d_t_vals.p);
-        CU(cudaGetLastError());
-        ctx->launches++;
-        keys = ctx->d_t_keys.p; vals = ctx->d_t_vals.p;
-        if (sort && n > 1) {  // per-rank lists are sorted; their union (rows dealt cyclically) is not
-            CU(ctx->d_t_keys_alt.ensure(n)); CU(ctx->d_t_vals_alt.ensure(n));
-            cub::DoubleBuffer<uint64_t> kb(ctx->d_t_keys.p, ctx->d_t_keys_alt.p);
-            cub::DoubleBuffer<uint32_t> vb(ctx->d_t_vals.p, ctx->d_t_vals_alt.p);
-            const int end_bit = std::min(64, 32 + bits_for(ctx->n));
-            size_t tmp = 0;
-            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
-            CU(ctx->d_tmp.ensure(tmp));
-            CU(cub::DeviceRadixSort::SortPairs(ctx->d_tmp.p, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
-            keys = kb.Current(); vals = vb.Current();
-        }
-    } else {
-        n = ctx->rec_n;
-        if (n == 0) return ASB_OK;
-        keys = ctx->rec_keys; vals = ctx->rec_vals;
-    }
+    const uint64_t n = count;
+    if (n == 0) return ASB_OK;
+    const uint64_t* keys = ctx->rec_keys + first;
+    const uint32_t* vals = ctx->rec_vals + first;
     if (ctx->n_lines + n > 0xFFFFFFF0ull) return fail(ctx, ASB_E_ARG, "more than 2^32 lines are not supported");
     const size_t total = (size_t)(ctx->n_lines + n);
     CU(grow_keep(ctx->d_la, total, ctx->n_lines, ctx->stream)); CU(grow_keep(ctx->d_lb, total, ctx->n_lines, ctx->stream));

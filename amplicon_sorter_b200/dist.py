@@ -297,7 +297,8 @@ def _run_shard_text(engine, job, dev, r, w, text_tables, sink):
         if r == 0 and merged is not None and merged.shape[0]:
             n_rec += int(merged.shape[0])
             try:
-                sink(engine.text_step_tensor(merged, sort=w > 1))
+                for chunk in engine.text_chunks_tensor(merged, sort=w > 1):
+                    sink(chunk)
             except Exception:  # noqa: BLE001 -- the next gather_step tells the other ranks
                 import traceback
 

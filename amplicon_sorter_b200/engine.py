@@ -53,8 +53,8 @@ class EngineBase:
             for k in TOTALS:
                 tot[k] += info.get(k, 0)
             tot["steps"] += 1
-            if info["n_records"]:
-                sink(self.text_step(info["n_records"]))
+            for chunk in self.text_chunks(info["n_records"]):
+                sink(chunk)
         return tot
 
 
@@ -234,14 +234,22 @@ class Engine(EngineBase):
             sl.ptr, sl.cap = p.value, want
         return sl
 
-    def text_step(self, n_records: int, dev_ptr: int | None = None, sort: bool = False) -> TextChunk:
-        """Lines of the last step's records (dev_ptr None) or of n_records asb_records in device memory at dev_ptr."""
-        sl = self._acquire_slot(_ffi.TEXT_MAX_LINE * int(n_records) + 64)
+    def text_step(self, first: int, count: int) -> TextChunk:
+        """Lines of records [first, first + count) of the current record set (the last step's, or text_load's)."""
+        sl = self._acquire_slot(_ffi.TEXT_MAX_LINE * int(count) + 64)
         nb = C.c_uint64()
-        self._check(self._lib.asb_text_step(self._h, C.c_void_p(dev_ptr) if dev_ptr else None, int(n_records), int(bool(sort)),
-                                            C.c_void_p(sl.ptr), sl.cap, C.byref(nb)))
+        self._check(self._lib.asb_text_step(self._h, int(first), int(count), C.c_void_p(sl.ptr), sl.cap, C.byref(nb)))
         sl.free.clear()
         return TextChunk(memoryview((C.c_char * nb.value).from_address(sl.ptr)).cast("B"), sl)
+
+    def text_chunks(self, n_records: int):
+        """The current record set as text, in chunks of at most TEXT_CHUNK records, in file order."""
+        for first in range(0, int(n_records), _ffi.TEXT_CHUNK):
+            yield self.text_step(first, min(_ffi.TEXT_CHUNK, int(n_records) - first))
+
+    def text_load(self, dev_ptr: int, n_records: int, sort: bool = True):
+        """Make n_records asb_records in device memory at dev_ptr the current record set (sorted if asked)."""
+        self._check(self._lib.asb_text_load(self._h, C.c_void_p(dev_ptr), int(n_records), int(bool(sort))))
 
     def step_records_tensor(self, n_records: int, dev):
         """The last step's records as an (n, 4) int32 tensor on this engine's GPU (for the NCCL gather)."""
@@ -252,8 +260,12 @@ class Engine(EngineBase):
             self.batch_records_dev(t.data_ptr())
         return t
 
-    def text_step_tensor(self, recs, sort: bool = True) -> TextChunk:
-        return self.text_step(int(recs.shape[0]), recs.data_ptr(), sort)
+    def text_chunks_tensor(self, recs, sort: bool = True):
+        """Lines of an (n, 4) int32 tensor of records on this engine's GPU (the NCCL gather of several ranks' lists)."""
+        n = int(recs.shape[0])
+        if n:
+            self.text_load(recs.data_ptr(), n, sort)
+        return self.text_chunks(n)
 
     def lines_hist(self):
         """(hist[1001] of iden*1000 over the resident lines, device ms)."""

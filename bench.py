@@ -51,8 +51,12 @@ ALU_OPS_PER_WORD_UPDATE = 10  # ALU-pipe instructions per Myers word-update in a
 # sampled rows matched the oracle (tests/test_gpu_fullsize.py); every later run -- any kernel version, any number of
 # GPUs -- must reproduce it.  None = no constant recorded for that config yet (the run prints its CRC).
 KNOWN_TEXT_CRC = {
-    5: 1976580653,  # 24,887,125 lines, 539,029,280 bytes (r2, 1 x B200; same line count as every r1 kernel version)
-}
+    1: 1131388478,  # 99,424 lines (the count of the unmodified script's own run), 1,756,869 bytes
+    2: 3681597654,  # 4,527,411 lines, 88,959,979 bytes
+    3: 3356075816,  # 916,299 lines, 17,988,322 bytes
+    4: 3352788876,  # 62,448,413 lines, 1,339,098,740 bytes
+    5: 1976580653,  # 24,887,125 lines, 539,029,280 bytes (same line count as every r1 kernel version)
+}  # all recorded before the pivot bound (asb_prune) existed: every pair went through the banded passes
 DESCR = {
     1: "cfg1: default batch mode on 1,000 synthetic ~700 bp reads (5 templates)",
     2: "cfg2: --all on 10,000 synthetic reads, 3 genes (1.8 / 0.7 / 1.0 kb) x 4 species",

@@ -115,15 +115,16 @@ int64_t asb_format_records(const asb_record *recs, uint64_t n, const uint32_t *i
  * (:560-561) printed for sorted position p, and the caller's iden strings -- Python's own str(round(1 - d/L, 3)) --
  * string number lbase[L] + d at sbuf[soff[e] .. soff[e+1]) (lbase[L] = 0xFFFFFFFF: no string for that length) with
  * milli[e] = iden * 1000.  It also empties the context's resident line set (asb_lines_*): a new tempfile starts.
- * asb_text_step turns sorted records into lines "idxA:idxB:iden[:reverse]\n" in (i_pos, j_pos) order, copies the text
- * to host_dst (cap bytes; pinned memory from asb_host_alloc makes the copy asynchronous-capable) and APPENDS the same
- * lines in integer form to the resident line set, so SSG / the best-hit filters run without parsing the file.
- *   dev_recs == NULL : the records of the last asb_batch_step (already sorted);
- *   dev_recs != NULL : n records in DEVICE memory, e.g. the NCCL gather of several ranks' lists; sort != 0 orders them. */
+ * asb_text_step turns records [first, first + count) of the CURRENT record set into lines "idxA:idxB:iden[:reverse]\n"
+ * in (i_pos, j_pos) order, copies the text to host_dst (cap bytes; pinned memory from asb_host_alloc) and APPENDS the
+ * same lines in integer form to the resident line set, so SSG / the best-hit filters run without parsing the file.
+ * Call it with consecutive ranges (a writer thread appends one chunk while the next is assembled).  The current
+ * record set is the sorted output of the last asb_batch_step, or what asb_text_load staged: n records in DEVICE
+ * memory, e.g. the NCCL gather of several ranks' lists; sort != 0 orders them by (i_pos, j_pos) first. */
 int asb_text_begin(asb_ctx *ctx, const uint32_t *idx_sorted, uint32_t n_pos, const uint32_t *lbase, uint32_t lbase_len,
                    const uint32_t *soff, const uint16_t *milli, uint32_t n_strings, const char *sbuf, uint32_t sbuf_len);
-int asb_text_step(asb_ctx *ctx, const asb_record *dev_recs, uint64_t n, int sort, char *host_dst, uint64_t cap,
-                  uint64_t *nbytes);
+int asb_text_load(asb_ctx *ctx, const asb_record *dev_recs, uint64_t n, int sort);
+int asb_text_step(asb_ctx *ctx, uint64_t first, uint64_t count, char *host_dst, uint64_t cap, uint64_t *nbytes);
 /* Pinned host memory for the text (no context needed). */
 int asb_host_alloc(uint64_t bytes, void **out);
 void asb_host_free(void *p);

@@ -76,9 +76,10 @@ def test_text_step_on_gathered_records_sorts_them(engine):
     engine.text_begin(*host.text_tables(order, lens_sorted, dpass))
     allr = np.concatenate(parts[::-1])  # rank order reversed: nothing may depend on it
     t = torch.from_numpy(allr.view(np.uint32).reshape(-1, 4).view(np.int32).copy()).cuda()
-    chunk = engine.text_step_tensor(t, sort=True)
-    got = bytes(chunk.data)
-    chunk.release()
+    got = b""
+    for chunk in engine.text_chunks_tensor(t, sort=True):
+        got += bytes(chunk.data)
+        chunk.release()
     want, _, _ = oracle_text(reads, np.arange(len(reads)))
     assert got == want
 
@@ -97,7 +98,9 @@ def test_text_errors_are_reported(engine):
     info = engine.batch_step()
     assert info["n_records"] > 0
     with pytest.raises(EngineError):
-        engine.text_step(info["n_records"])
+        engine.text_step(0, info["n_records"])
+    with pytest.raises(EngineError):  # a range outside the current record set
+        engine.text_step(info["n_records"], 1)
 
 
 def test_process_list_writes_the_file_and_leaves_resident_lines(engine, tmp_path):
