@@ -316,8 +316,14 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? 4 : 1) asb_screen(c
 // asb_lists: persistent warps pull 32-entry slices of a (row, column)-sorted list; a slice that
 // spans several rows is processed one row-run at a time.
 // --------------------------------------------------------------------------------------------
+#ifndef ASB_LISTS_MINB9
+#define ASB_LISTS_MINB9 0
+#endif
+#ifndef ASB_WIDE_WARPS
+#define ASB_WIDE_WARPS 4  // measured (cfg5, zone pass): 4-warp blocks + the 20-word class 412 ms vs 458 ms per job
+#endif
 template <int BT>
-__global__ void __launch_bounds__(256) asb_lists(const DevBatch B, const int mode)
+__global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? ASB_LISTS_MINB9 : 0) asb_lists(const DevBatch B, const int mode)
 {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -665,7 +671,7 @@ using namespace asb;
 
 namespace {
 
-constexpr int kClasses[] = {5, 9, 13, 17, 24, 32, 40, 0};
+constexpr int kClasses[] = {5, 9, 13, 17, 20, 24, 32, 40, 0};
 constexpr int kNumClasses = sizeof(kClasses) / sizeof(int);
 constexpr int kWarpsPerBlock = 8;
 
@@ -676,7 +682,7 @@ template <int... Bs> struct FnTable {
     static screen_fn screen(int idx) { static const screen_fn t[] = {asb_screen<Bs>...}; return t[idx]; }
     static lists_fn lists(int idx) { static const lists_fn t[] = {asb_lists<Bs>...}; return t[idx]; }
 };
-using Fns = FnTable<5, 9, 13, 17, 24, 32, 40, 0>;
+using Fns = FnTable<5, 9, 13, 17, 20, 24, 32, 40, 0>;
 
 int class_for(int need)
 {
@@ -846,9 +852,9 @@ struct LaunchShape { int warps; size_t smem; int grid; };
 
 // Every warp owns a Peq table of (sigma+1) x Wpad words.  8 warps per block normally; large alphabets or
 // very long reads fall back to fewer warps per block so that the tables still fit in shared memory.
-template <typename F> int launch_cfg(asb_ctx* ctx, F fn, const DevBatch& B, LaunchShape* shape)
+template <typename F> int launch_cfg(asb_ctx* ctx, F fn, const DevBatch& B, LaunchShape* shape, int max_warps = kWarpsPerBlock)
 {
-    for (int warps = kWarpsPerBlock; warps >= 1; warps >>= 1) {
+    for (int warps = max_warps; warps >= 1; warps >>= 1) {
         const size_t smem = (size_t)warps * B.warp_words * sizeof(uint32_t);
         if (smem > 227 * 1024) continue;
         CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -868,7 +874,8 @@ int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint3
     CU(cudaMemsetAsync(ctx->d_ctr.p + C_TASK, 0, sizeof(unsigned long long), ctx->stream));
     lists_fn fn = Fns::lists(cls);
     LaunchShape ls;
-    int rc = launch_cfg(ctx, fn, B, &ls);
+    // wide windows are register-bound (one 256-thread block per SM): smaller blocks pack the register file better
+    int rc = launch_cfg(ctx, fn, B, &ls, kClasses[cls] >= 17 ? ASB_WIDE_WARPS : kWarpsPerBlock);
     if (rc) return rc;
     const uint64_t slices = (n + 31) / 32, blocks = (slices + ls.warps - 1) / ls.warps;
     const int grid = (int)std::min<uint64_t>((uint64_t)ls.grid, std::max<uint64_t>(blocks, 1));
@@ -990,7 +997,7 @@ __global__ void __launch_bounds__(256) asb_cl_matrix_kernel(const int32_t* __res
 namespace {
 
 constexpr uint32_t kClMaxPivots = 1024;   // 12 bits in the cluster word would allow 4095; the pivot matrix is m x m x 2 alignments
-constexpr uint32_t kClRound = 64;         // candidate pivots per round
+constexpr uint32_t kClRound = 128;        // candidate pivots per round
 
 // Capped exact distances of the entries (keys[e] = query << 32 | target read id, st[e] = target strand) already in
 // DEVICE memory: out[e] = d if d <= cap, else -1.  Positions are read ids (the batch's own arrays stay untouched).
@@ -1213,7 +1220,19 @@ int asb_set_param(asb_ctx* ctx, const char* name, double value)
     return ASB_OK;
 }
 
+static int upload_impl(asb_ctx* ctx, const uint8_t* ascii, bool ascii_on_device, const uint64_t* offs, uint32_t n_reads);
+
 int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, uint32_t n_reads)
+{
+    return upload_impl(ctx, ascii, false, offs, n_reads);
+}
+
+int asb_upload_reads_dev(asb_ctx* ctx, const uint8_t* dev_ascii, const uint64_t* offs, uint32_t n_reads)
+{
+    return upload_impl(ctx, dev_ascii, true, offs, n_reads);
+}
+
+static int upload_impl(asb_ctx* ctx, const uint8_t* ascii, bool ascii_on_device, const uint64_t* offs, uint32_t n_reads)
 {
     if (!ctx || !offs || (!ascii && n_reads && offs[n_reads])) return fail(ctx, ASB_E_ARG, "null argument");
     CU(cudaSetDevice(ctx->device));
@@ -1239,15 +1258,17 @@ int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, u
     // staging buffers live in the context: a cudaMalloc / cudaFree pair per upload costs more than the upload itself
     DevBuf<uint8_t>& d_ascii = ctx->d_up_ascii; DevBuf<uint64_t>& d_offs = ctx->d_up_offs; DevBuf<uint64_t>& d_roff = ctx->d_up_roff;
     DevBuf<uint32_t>& d_present = ctx->d_up_present; DevBuf<uint8_t>& d_maps = ctx->d_up_maps;
-    CU(d_ascii.ensure(nbytes + 1)); CU(d_offs.ensure((size_t)n_reads + 1)); CU(d_roff.ensure((size_t)n_reads + 1));
+    if (!ascii_on_device) CU(d_ascii.ensure(nbytes + 1));
+    CU(d_offs.ensure((size_t)n_reads + 1)); CU(d_roff.ensure((size_t)n_reads + 1));
     CU(d_present.ensure(8)); CU(d_maps.ensure(512));
     CU(ctx->d_cf.ensure(total)); CU(ctx->d_cr.ensure(total));
-    if (nbytes) CU(cudaMemcpyAsync(d_ascii.p, ascii, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t* src_ascii = ascii_on_device ? ascii : d_ascii.p;  // e.g. the buffer an NCCL broadcast just filled
+    if (nbytes && !ascii_on_device) CU(cudaMemcpyAsync(d_ascii.p, ascii, nbytes, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d_offs.p, offs, sizeof(uint64_t) * ((size_t)n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d_roff.p, ctx->h_roff.data(), sizeof(uint64_t) * ((size_t)n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(d_present.p, 0, 32, ctx->stream));
     if (nbytes) {
-        asb_alpha_scan<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_ascii.p, nbytes, d_present.p);
+        asb_alpha_scan<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(src_ascii, nbytes, d_present.p);
         CU(cudaGetLastError());
     }
     uint32_t present[8];
@@ -1271,7 +1292,7 @@ int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, u
     CU(cudaMemsetAsync(ctx->d_cr.p, (int)sigma, total, ctx->stream));
     if (n_reads) {
         asb_encode<<<std::min<uint32_t>(n_reads, (uint32_t)ctx->sm_count * 16), 256, 0, ctx->stream>>>(
-            d_ascii.p, d_offs.p, d_roff.p, n_reads, d_maps.p, d_maps.p + 256, (uint8_t)sigma, ctx->d_cf.p, ctx->d_cr.p);
+            src_ascii, d_offs.p, d_roff.p, n_reads, d_maps.p, d_maps.p + 256, (uint8_t)sigma, ctx->d_cf.p, ctx->d_cr.p);
         CU(cudaGetLastError());
     }
     CU(cudaStreamSynchronize(ctx->stream));

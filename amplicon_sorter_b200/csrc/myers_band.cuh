@@ -138,7 +138,10 @@ __device__ __forceinline__ uint32_t asb_add(uint32_t a, uint32_t b) { uint32_t r
 #endif
 
 // Granularity of the straight-line variants: active lengths are rounded up to BT - j*step.
-__host__ __device__ constexpr int len_step(int BT) { return BT <= 9 ? 1 : (BT <= 17 ? 2 : 4); }
+#ifndef ASB_STEP_WIDE
+#define ASB_STEP_WIDE 4
+#endif
+__host__ __device__ constexpr int len_step(int BT) { return BT <= 9 ? 1 : (BT <= 17 ? 2 : ASB_STEP_WIDE); }
 
 // 32 columns over the first LEN words of the window, straight-line (no per-word control flow).
 template <int LEN, int NB>

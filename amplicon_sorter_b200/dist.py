@@ -51,8 +51,8 @@ def init_from_env(backend: str | None = None):
     return rank(), w, dev
 
 
-def _bcast_array(arr, dev, src=0):
-    """Broadcast a numpy array (shape/dtype known on src only)."""
+def _bcast_array(arr, dev, src=0, keep_on_device=False):
+    """Broadcast a numpy array (shape/dtype known on src only).  keep_on_device: return the uint8 tensor on `dev`."""
     import torch
     import torch.distributed as dist
 
@@ -62,11 +62,17 @@ def _bcast_array(arr, dev, src=0):
     dist.broadcast_object_list(meta, src=src)
     shape, dt = meta[0]
     if dist.get_rank() == src:
-        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(dev)
+        import warnings
+
+        with warnings.catch_warnings():  # a read-only view of a bytes object: it is only read (copied to `dev`)
+            warnings.simplefilter("ignore", UserWarning)
+            t = torch.from_numpy(np.ascontiguousarray(arr).view(np.uint8).reshape(-1)).to(dev)
     else:
         t = torch.empty(int(np.prod(shape)) * np.dtype(dt).itemsize, dtype=torch.uint8, device=dev)
     if t.numel():
         dist.broadcast(t, src=src)
+    if keep_on_device:
+        return t
     return t.cpu().numpy().view(np.dtype(dt)).reshape(shape)
 
 
@@ -81,7 +87,8 @@ def broadcast_job(job: dict | None, dev):
     out = {}
     for k, is_arr in keys[0]:
         if is_arr:
-            out[k] = _bcast_array(job[k] if job is not None else None, dev)
+            # the read bytes go straight from the broadcast buffer into the engine (no host round trip on any rank)
+            out[k] = _bcast_array(job[k] if job is not None else None, dev, keep_on_device=(k == "buf" and dev.type == "cuda"))
         else:
             box = [job[k] if job is not None else None]
             dist.broadcast_object_list(box, src=0)
@@ -181,7 +188,7 @@ class ShardedEngine(EngineBase):
 
     def upload_reads(self, buf, offs):
         job = broadcast_job({"op": "upload", "buf": np.ascontiguousarray(buf), "offs": np.ascontiguousarray(offs)}, self.dev)
-        self._guard(lambda: self.engine.upload_reads(job["buf"], job["offs"]), "upload_reads")
+        self._guard(lambda: _upload(self.engine, job), "upload_reads")
 
     def set_param(self, name, value):
         broadcast_job({"op": "param", "name": name, "value": float(value)}, self.dev)
@@ -231,6 +238,13 @@ class ShardedEngine(EngineBase):
         if not self.aborted:
             broadcast_job({"op": "stop"}, self.dev)
         self.engine.close()
+
+
+def _upload(engine, job):
+    if isinstance(job["buf"], np.ndarray):
+        engine.upload_reads(job["buf"], job["offs"])
+    else:
+        engine.upload_reads_tensor(job["buf"], job["offs"])
 
 
 def _run_shard(engine, job, dev, r, w):
@@ -379,7 +393,7 @@ def worker_loop(engine, dev):
             engine.close()
             return
         if op == "upload":
-            facade._guard(lambda: engine.upload_reads(job["buf"], job["offs"]), "upload_reads")
+            facade._guard(lambda: _upload(engine, job), "upload_reads")
         elif op == "param":
             engine.set_param(job["name"], job["value"])
         elif op == "batch":

@@ -119,6 +119,14 @@ class Engine(EngineBase):
         self.n_reads = n
         self._lens = (offs[1:] - offs[:-1]).astype(np.uint32)
 
+    def upload_reads_tensor(self, t, offs: np.ndarray):
+        """upload_reads with the read bytes already on this engine's GPU (a uint8 torch tensor)."""
+        offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        n = offs.shape[0] - 1
+        self._check(self._lib.asb_upload_reads_dev(self._h, C.c_void_p(t.data_ptr()), ptr(offs, C.c_uint64), n))
+        self.n_reads = n
+        self._lens = (offs[1:] - offs[:-1]).astype(np.uint32)
+
     def debug_read(self, r: int, strand: int = 0) -> bytes:
         out = np.empty(int(self._lens[r]), dtype=np.uint8)
         self._check(self._lib.asb_debug_read(self._h, r, strand, ptr(out, C.c_uint8), out.shape[0]))

@@ -119,6 +119,22 @@ def text_tables(idx_sorted: np.ndarray, lens_sorted: np.ndarray, dpass: np.ndarr
     return np.ascontiguousarray(idx_sorted, dtype=np.uint32), lbase, soff, milli, "".join(strs).encode("ascii")
 
 
+def ascii_view(s: str) -> np.ndarray:
+    """The bytes of `s` as a uint8 array.  Reads are ASCII, and CPython keeps an ASCII str as one byte per character:
+    PyUnicode_AsUTF8AndSize then returns the str's own buffer, so 100 MB of reads are not copied a second time.  Any
+    other text (the reference would accept it: every distinct character is a symbol) takes the latin-1 copy."""
+    import ctypes as C
+
+    if s.isascii():
+        size = C.c_ssize_t()
+        fn = C.pythonapi.PyUnicode_AsUTF8AndSize
+        fn.restype, fn.argtypes = C.c_void_p, [C.py_object, C.POINTER(C.c_ssize_t)]
+        p = fn(s, C.byref(size))
+        if p and size.value == len(s):
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(len(s),)) if len(s) else np.zeros(0, np.uint8)
+    return np.frombuffer(s.encode("latin-1"), dtype=np.uint8)
+
+
 class TextSink:
     """Appends the slabs of text to the tempfile on a writer thread, so that write(2) of one slab overlaps the GPU
     work on the next (the reference appends per 1 M-pair chunk, amplicon_sorter.py:802-807).  Callable: sink(chunk)."""
@@ -171,11 +187,13 @@ class AllPairs:
                       "word_updates": 0, "gpu_ms": 0.0, "screen_ms": 0.0}
 
     def upload(self, seqs: list[str]):
-        lens = np.fromiter((len(s) for s in seqs), dtype=np.uint64, count=len(seqs))
+        lens = np.fromiter(map(len, seqs), dtype=np.uint64, count=len(seqs))
         offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
         np.cumsum(lens, out=offs[1:])
-        buf = np.frombuffer("".join(seqs).encode("latin-1"), dtype=np.uint8)
+        self._joined = "".join(seqs)  # kept alive: `buf` may be a view of it
+        buf = ascii_view(self._joined)
         self.engine.upload_reads(buf, offs)
+        self._joined = None
         self.lens = lens.astype(np.int64)
 
     def _account(self, tot):
@@ -221,13 +239,21 @@ class AllPairs:
 
     def compare_to_file(self, order, lens_sorted, hi, idx_sorted, similar_genes: float, out_path: str):
         """Decide every pair of the planned batch and append the lines to `out_path` as they are produced."""
+        import time
+
+        t0 = time.perf_counter()
         dpass, drev = thresholds.tables(similar_genes / 100, int(lens_sorted.max()) + 1)  # similarg :783
         tables = text_tables(idx_sorted, lens_sorted, dpass)
+        t1 = time.perf_counter()
         sink = TextSink(out_path)
         try:
             tot = self.engine.compare_text(order, hi, dpass, drev, tables, sink)
+            t2 = time.perf_counter()
         finally:
             sink.close()
+        t3 = time.perf_counter()
+        self.stats["phases_ms"] = {"cut-off + iden string tables": (t1 - t0) * 1e3, "all slabs (GPU)": (t2 - t1) * 1e3,
+                                   "of which pivots + read assignment": tot.get("cluster_ms", 0.0), "writer thread drain": (t3 - t2) * 1e3}
         self._account(tot)
         self.stats["text_bytes"] = self.stats.get("text_bytes", 0) + sink.bytes
         return tot
@@ -266,27 +292,22 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
     except FileNotFoundError:
         pass
 
+    import time
+
+    t0 = time.perf_counter()
     # distinct records of all batches, keyed by their idx field (:560-561); -ra batches overlap
-    idx_to_rid: dict = {}
-    seqs: list = []
-    batch_rids = []
-    for d in self:
-        rids = np.empty(len(d), dtype=np.int64)
-        for t, rec in enumerate(d):
-            key = rec[3]
-            rid = idx_to_rid.get(key)
-            if rid is None:
-                rid = len(seqs)
-                idx_to_rid[key] = rid
-                seqs.append(rec[1])
-            rids[t] = rid
-        batch_rids.append(rids)
-    rid_to_idx = np.fromiter(idx_to_rid.keys(), dtype=np.int64, count=len(seqs))  # dicts keep insertion order = rid order
+    flat = [rec for d in self for rec in d]
+    keys = np.fromiter((rec[3] for rec in flat), dtype=np.int64, count=len(flat))
+    rid_to_idx, first, inv = np.unique(keys, return_index=True, return_inverse=True)  # read id = rank of the idx value
+    seqs = [flat[i][1] for i in first.tolist()]
+    batch_rids = np.split(inv.astype(np.int64), np.cumsum([len(d) for d in self])[:-1]) if len(self) else []
 
     from . import groups
 
     ap = AllPairs(engine, device)
+    t1 = time.perf_counter()
     ap.upload(seqs)
+    t2 = time.perf_counter()
     live = [(d, rids) for d, rids in zip(self, batch_rids) if len(d)]
     perms, order, lens_sorted, hi, tl_total = ap.plan([rids for _, rids in live])
     for (d, _), perm in zip(live, perms):
@@ -294,11 +315,15 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
     for old, _ in groups.CACHE.values():  # lines of an earlier input file are never asked for again (:2179 deletes that file)
         old.discard()
     groups.CACHE.clear()
+    t3 = time.perf_counter()
     if tl_total:
         # records come out sorted by (global i, global j) = (batch, i, j): the reference's -np 1 file order
         ap.compare_to_file(order, lens_sorted, hi, rid_to_idx[order.astype(np.int64)], args.similar_genes, out_path)
         # the consumers of the file (SSG, update_list, read_indexes) get its lines without parsing the text
         groups.CACHE[os.path.abspath(out_path)] = (groups.DeviceLines(ap.engine), os.path.getsize(out_path))
+    t4 = time.perf_counter()
+    ap.stats["phases_ms"] = {"records -> read set": (t1 - t0) * 1e3, "join + upload": (t2 - t1) * 1e3, "sort + windows": (t3 - t2) * 1e3,
+                             "compare + write": (t4 - t3) * 1e3, **ap.stats.get("phases_ms", {})}
     if stats_out is not None:
         stats_out.update(ap.stats)
         stats_out["tl"] = tl_total

@@ -379,6 +379,7 @@ def main():
                "h2d_bytes_per_step": int((w["buf"].nbytes + w["offs"].nbytes + small) * world + sum(np.asarray(t).nbytes if not isinstance(t, bytes) else len(t) for t in w["tables"])),
                "d2h_bytes_per_step": int(fbytes), "steps": a.e2e_steps, "ms_per_step": t_e2e / a.e2e_steps * 1e3,
                "tempfile_bytes": int(fbytes), "tempfile_crc32": crc,
+               "rank0_phases_ms_last_step": {k: round(v, 1) for k, v in stats.get("phases_ms", {}).items()},
                "api": "host.process_list(comparelist2, tempfile) -- the drop-in for amplicon_sorter.py:647 -- "
                       + ("on one Engine" if world == 1 else f"on dist.ShardedEngine over {world} ranks (NCCL broadcast of the job, per-slab device-side gather)")
                       + ": str join + H2D of the reads, all slabs, text assembled on the GPU, D2H, write(2) on a writer thread"}

@@ -86,6 +86,9 @@ int asb_set_param(asb_ctx *ctx, const char *name, double value);
  * the data (edlib semantics: every distinct character is its own symbol) and the forward and
  * compl_reverse symbol codes in HBM.  Buffers are caller-owned and copied during the call. */
 int asb_upload_reads(asb_ctx *ctx, const uint8_t *ascii, const uint64_t *offs, uint32_t n_reads);
+/* Same, with the read bytes already in DEVICE memory of the context's GPU (offs stays a host array): the buffer an
+ * NCCL broadcast of the job just filled on a worker rank. */
+int asb_upload_reads_dev(asb_ctx *ctx, const uint8_t *dev_ascii, const uint64_t *offs, uint32_t n_reads);
 
 /* Replaces process_list.queuer (:662-715) for one batch -- or for several batches laid end to end
  * (a row's window (p, hi[p]] never leaves its batch; lengths must be non-decreasing inside every window).

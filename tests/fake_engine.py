@@ -68,8 +68,8 @@ class OracleEngine(EngineBase):
         return tuple(self._res)
 
     def upload_reads(self, buf, offs):
-        self.buf = np.ascontiguousarray(buf, dtype=np.uint8)
-        self.offs = np.ascontiguousarray(offs, dtype=np.uint64)
+        self.buf = np.array(buf, dtype=np.uint8)    # "buffers are caller-owned and copied during the call" (asb200.h)
+        self.offs = np.array(offs, dtype=np.uint64)
 
     def set_param(self, *a):
         pass

@@ -32,7 +32,7 @@ def _worker(rank, world, port, fixture, outdir):
     host.process_list(batches, os.path.join(outdir, "x_compare.tmp"), args, engine=sharded, stats_out=stats)
     sharded.close()
     with open(os.path.join(outdir, "stats.json"), "w") as f:
-        json.dump({k: (int(v) if isinstance(v, (int, np.integer)) else float(v)) for k, v in stats.items()}, f)
+        json.dump({k: (int(v) if isinstance(v, (int, np.integer)) else float(v)) for k, v in stats.items() if not isinstance(v, dict)}, f)
 
 
 @pytest.mark.parametrize("name", ["g1_default", "g3_all_mixed"])
