@@ -758,8 +758,11 @@ struct asb_ctx {
     DevBuf<uint64_t> d_t_keys, d_t_keys_alt, d_t_off;
     uint32_t t_n_pos = 0, t_lbase_len = 0, t_n_strings = 0;
     bool text_ready = false, lines_have_rev = false;
+    cudaStream_t tstream = nullptr; cudaEvent_t tev = nullptr; unsigned long long* h_tctr = nullptr;  // the text stage's own stream (text.cuh)
+    DevBuf<uint8_t> d_t_tmp; DevBuf<unsigned long long> d_t_err;
+    const uint64_t* t_keys = nullptr; const uint32_t* t_vals = nullptr; uint64_t t_rec_n = 0;  // records staged by asb_text_load
     // cluster pruning (ensure_clusters): per-read cluster words, pivot x pivot lower bounds, and what the batch decided
-    DevBuf<uint32_t> d_cword, d_cl_u, d_cl_piv; DevBuf<uint16_t> d_pivD; DevBuf<uint64_t> d_cl_keys; DevBuf<uint8_t> d_cl_st; DevBuf<int32_t> d_cl_out;
+    DevBuf<uint32_t> d_cword, d_cl_u, d_cl_piv, d_cl_best, d_cl_pb, d_cl_vals; DevBuf<uint16_t> d_pivD; DevBuf<uint64_t> d_cl_keys; DevBuf<uint8_t> d_cl_st; DevBuf<int32_t> d_cl_out;
     int prune = 1;              // parameter "prune": 0 = never
     uint32_t prune_min_reads = 1024; uint64_t prune_min_pairs = 1ull << 22;  // below these a job is a few milliseconds anyway
     bool cl_ready = false; uint32_t cl_kmax = 0, cl_npiv = 0, cl_covered = 0;
@@ -918,9 +921,9 @@ void fill_base2(const asb_ctx* ctx, uint8_t* base2)
 }
 
 // Builds the seed tables of the uploaded reads once per upload (first step that wants them).
-int ensure_seeds(asb_ctx* ctx)
+int ensure_seeds(asb_ctx* ctx, bool force = false)
 {
-    if (!ctx->seed_lb || ctx->seeds_ready || ctx->n_reads == 0) return ASB_OK;
+    if ((!ctx->seed_lb && !force) || ctx->seeds_ready || ctx->n_reads == 0) return ASB_OK;
     const uint32_t n = ctx->n_reads;
     std::vector<uint32_t> off((size_t)n + 1, 0);
     for (uint32_t r = 0; r < n; ++r) {
@@ -992,6 +995,99 @@ __global__ void __launch_bounds__(256) asb_cl_matrix_kernel(const int32_t* __res
         D[e] = (uint16_t)(out[e] >= 0 ? (uint32_t)out[e] : cap + 1u);
 }
 
+// ---- K3 put to work: shared 7-mer counts as the SCHEDULER of the pivot assignment (never a decision) ----
+// The q-mer presence bitsets of the seed tables (4^7 bits per read, forward strand) are the north star's "presence
+// bitsets held in HBM".  A read that belongs to a pivot's cluster shares ~40 % of its 7-mers with the pivot (in the
+// right orientation), an unrelated read ~6 %: popcount(bits_read & bits_pivot) over the new pivots of a round picks,
+// for every uncovered read, the ONE (pivot, orientation) worth an exact alignment -- instead of aligning every read
+// against every pivot on both strands.  A wrong pick costs nothing but a lost opportunity to prune: the read stays
+// uncovered, its pairs go through the exact passes.
+
+// presence bitset of the compl_reverse strand of the round's pivots: PB[(p * 2 + 1)][..]; PB[(p * 2 + 0)] = the pivot's own
+__global__ void __launch_bounds__(256) asb_cl_pivbits_kernel(const uint8_t* __restrict__ cr, const uint64_t* __restrict__ roff, const uint32_t* __restrict__ rlen,
+                                                           const uint8_t* __restrict__ base2, const uint32_t* __restrict__ qbits,
+                                                           const uint32_t* __restrict__ piv, uint32_t np, uint32_t* __restrict__ PB)
+{
+    __shared__ uint32_t sm[kSeedWords];
+    for (uint32_t p = blockIdx.x; p < np; p += gridDim.x) {
+        const uint32_t r = piv[p];
+        for (int w = threadIdx.x; w < kSeedWords; w += blockDim.x) { sm[w] = 0u; PB[((size_t)p * 2) * kSeedWords + w] = qbits[(size_t)r * kSeedWords + w]; }
+        __syncthreads();
+        const uint8_t* v = cr + roff[r];
+        const int len = (int)rlen[r];
+        for (int q = threadIdx.x; q + kSeedQ <= len; q += blockDim.x) {
+            uint32_t code = 0;
+            bool ok = true;
+#pragma unroll
+            for (int t = 0; t < kSeedQ; ++t) { const uint32_t b = base2[v[q + t]]; ok = ok && b < 4u; code = (code << 2) | (b & 3u); }
+            if (ok) atomicOr(&sm[code >> 5], 1u << (code & 31));
+        }
+        __syncthreads();
+        for (int w = threadIdx.x; w < kSeedWords; w += blockDim.x) PB[((size_t)p * 2 + 1) * kSeedWords + w] = sm[w];
+        __syncthreads();
+    }
+}
+
+// Tile of 32 pivot-orientations in shared memory (rows padded to an odd stride: lane l walks row l), one warp per
+// read: the read's bitset word is a broadcast, every lane accumulates the count of ITS pivot-orientation, the warp's
+// arg-max goes to best[u] = count << 16 | (p * 2 + orientation) with one atomicMax.  POPC / LDS bound.
+constexpr int kClTile = 32;
+__global__ void __launch_bounds__(256) asb_cl_screen_kernel(const uint32_t* __restrict__ qbits, const uint32_t* __restrict__ reads, uint32_t nu,
+                                                          const uint32_t* __restrict__ PB, uint32_t nps, uint32_t* __restrict__ best)
+{
+    extern __shared__ uint32_t sm[];
+    uint32_t* tile = sm;                                        // [kClTile][kSeedWords + 1]
+    uint32_t* rd = sm + kClTile * (kSeedWords + 1);             // [8 warps][kSeedWords]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t ps0 = blockIdx.y * kClTile;
+    for (uint32_t x = threadIdx.x; x < kClTile * kSeedWords; x += blockDim.x) {
+        const uint32_t row = x / kSeedWords, w = x % kSeedWords;
+        tile[row * (kSeedWords + 1) + w] = ps0 + row < nps ? __ldg(PB + (size_t)(ps0 + row) * kSeedWords + w) : 0u;
+    }
+    __syncthreads();
+    uint32_t* mine = rd + wid * kSeedWords;
+    const uint32_t* trow = tile + lane * (kSeedWords + 1);
+    for (uint32_t u = blockIdx.x * 8 + wid; u < nu; u += gridDim.x * 8) {
+        const uint32_t* q = qbits + (size_t)__ldg(reads + u) * kSeedWords;
+        __syncwarp();
+        for (int w = lane; w < kSeedWords; w += 32) mine[w] = __ldg(q + w);
+        __syncwarp();
+        uint32_t acc = 0;
+#pragma unroll 8
+        for (int w = 0; w < kSeedWords; ++w) acc += __popc(mine[w] & trow[w]);
+        uint32_t v = (min(acc, 0xFFFFu) << 16) | (ps0 + lane);
+        if (ps0 + lane >= nps) v = 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+        if (lane == 0 && v) atomicMax(best + u, v);
+    }
+}
+
+// the one (pivot, orientation) picked for every uncovered read -> entry of the exact list
+__global__ void __launch_bounds__(256) asb_cl_pick_kernel(const uint32_t* __restrict__ best, const uint32_t* __restrict__ reads, uint32_t nu,
+                                                        const uint32_t* __restrict__ piv, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
+        const uint32_t ps = best[u] & 0xFFFFu;
+        keys[u] = ((uint64_t)piv[ps >> 1] << 32) | reads[u];
+        vals[u] = ps;  // pivot of the round and orientation, travels through the sort
+    }
+}
+
+__global__ void __launch_bounds__(256) asb_cl_strand_kernel(const uint32_t* __restrict__ vals, uint32_t n, uint8_t* __restrict__ st)
+{
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) st[e] = (uint8_t)(vals[e] & 1u);
+}
+
+__global__ void __launch_bounds__(256) asb_cl_assign1_kernel(const int32_t* __restrict__ out, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                           uint32_t n, uint32_t piv_base, uint32_t* __restrict__ cword)
+{
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int d = out[e];
+        if (d >= 0) cword[(uint32_t)keys[e]] = ((piv_base + (vals[e] >> 1)) << 20) | ((vals[e] & 1u) << 19) | (uint32_t)d;
+    }
+}
+
 }  // namespace asb
 
 namespace {
@@ -1050,9 +1146,9 @@ int ensure_clusters(asb_ctx* ctx, uint32_t kmax)
     ctx->cl_ready = false; ctx->cl_npiv = 0; ctx->cl_covered = 0;
     const uint32_t n = ctx->n_reads;
     if (3ull * kmax + 1 > 65535ull || kmax >= (1u << 19)) return ASB_OK;  // distances would not fit the tables: no pruning
-    int rc = ensure_seeds(ctx);  // also uploads the read-id indexed offset / length arrays
+    int rc = ensure_seeds(ctx, true);  // the 7-mer bitsets schedule the assignment; also uploads the read-id indexed offset / length arrays
     if (rc) return rc;
-    if (!ctx->seeds_ready) {  // seed_lb off: the arrays are still needed
+    if (!ctx->seeds_ready) {  // no reads
         CU(ctx->d_roff_all.ensure((size_t)n + 1)); CU(ctx->d_rlen_all.ensure(n));
         CU(cudaMemcpyAsync(ctx->d_roff_all.p, ctx->h_roff.data(), sizeof(uint64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(ctx->d_rlen_all.p, ctx->h_rlen.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -1102,30 +1198,42 @@ int ensure_clusters(asb_ctx* ctx, uint32_t kmax)
         std::vector<uint32_t> acc;
         for (uint32_t a : acc_idx) acc.push_back(cand[a]);
         const uint32_t na = (uint32_t)acc.size();
-        // -- the uncovered reads against the new pivots: reads in length order, so that the 32 targets of a warp need
-        // the same window, padded to whole warps (a warp never mixes the longest reads of one pass with the shortest
-        // of the next)
+        // -- every uncovered read against the ONE new pivot (and orientation) its 7-mers point to
         const uint32_t base = (uint32_t)pivots.size();
-        std::vector<uint32_t> ul(uncovered);
-        std::stable_sort(ul.begin(), ul.end(), [ctx](uint32_t x, uint32_t y) { return ctx->h_rlen[x] < ctx->h_rlen[y]; });
-        const uint32_t nup = (nu + 31u) & ~31u;
-        ul.resize(nup, ul.back());
-        int need = 1;
-        for (uint32_t a : acc)
-            for (uint32_t u = 0; u < nup; u += 32)
-                need = std::max(need, slice_need((int)ctx->h_rlen[a], (int)ctx->h_rlen[ul[u]], (int)ctx->h_rlen[ul[u + 31]], (int)kmax));
-        CU(ctx->d_cl_u.ensure(std::max<uint32_t>(n + 32, nup)));
+        const uint32_t nps = 2 * na;
+        CU(ctx->d_cl_u.ensure((size_t)n + 32)); CU(ctx->d_cl_best.ensure(n)); CU(ctx->d_cl_pb.ensure((size_t)2 * kClRound * kSeedWords));
+        CU(ctx->d_cl_vals.ensure(n)); CU(ctx->d_cl_keys.ensure(n)); CU(ctx->d_cl_st.ensure(n)); CU(ctx->d_cl_out.ensure(n));
+        CU(ctx->d_alt.ensure(n)); CU(ctx->d_altv.ensure(n));
         CU(cudaMemcpyAsync(ctx->d_cl_piv.p + base, acc.data(), sizeof(uint32_t) * na, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_cl_u.p, ul.data(), sizeof(uint32_t) * nup, cudaMemcpyHostToDevice, ctx->stream));
-        total = (uint64_t)na * 2 * nup;
-        CU(ctx->d_cl_keys.ensure(total)); CU(ctx->d_cl_st.ensure(total)); CU(ctx->d_cl_out.ensure(total));
-        asb::asb_cl_gen_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(ctx->d_cl_piv.p + base, na, ctx->d_cl_u.p, nup, ctx->d_cl_keys.p, ctx->d_cl_st.p);
+        CU(cudaMemcpyAsync(ctx->d_cl_u.p, uncovered.data(), sizeof(uint32_t) * nu, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_cl_best.p, 0, sizeof(uint32_t) * nu, ctx->stream));
+        asb::asb_cl_pivbits_kernel<<<na, 256, 0, ctx->stream>>>(ctx->d_cr.p, ctx->d_roff_all.p, ctx->d_rlen_all.p, ctx->d_base2.p, ctx->d_qbits.p,
+                                                                ctx->d_cl_piv.p + base, na, ctx->d_cl_pb.p);
         CU(cudaGetLastError());
-        rc = capped_exact_dev(ctx, ctx->d_cl_keys.p, ctx->d_cl_st.p, total, (int)kmax, ctx->d_cl_out.p, need);
+        {
+            const size_t smem = (size_t)(asb::kClTile * (kSeedWords + 1) + 8 * kSeedWords) * sizeof(uint32_t);
+            CU(cudaFuncSetAttribute(asb::asb_cl_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint32_t tiles = (nps + asb::kClTile - 1) / asb::kClTile;
+            const uint32_t gx = std::max<uint32_t>(1, std::min<uint32_t>((nu + 7) / 8, (uint32_t)ctx->sm_count * 4 / std::max<uint32_t>(tiles, 1) + 1));
+            asb::asb_cl_screen_kernel<<<dim3(gx, tiles), 256, smem, ctx->stream>>>(ctx->d_qbits.p, ctx->d_cl_u.p, nu, ctx->d_cl_pb.p, nps, ctx->d_cl_best.p);
+            CU(cudaGetLastError());
+        }
+        asb::asb_cl_pick_kernel<<<grid_for(ctx, nu, 256), 256, 0, ctx->stream>>>(ctx->d_cl_best.p, ctx->d_cl_u.p, nu, ctx->d_cl_piv.p + base, ctx->d_cl_keys.p, ctx->d_cl_vals.p);
+        CU(cudaGetLastError());
+        uint64_t* skeys; uint32_t* svals;
+        {   // entries grouped by pivot: the 32 lanes of a list warp share their query
+            const uint32_t keep_n = ctx->n; ctx->n = std::max(ctx->n, n);  // sort_list sizes its key bits from ctx->n / n_reads
+            rc = sort_list(ctx, ctx->d_cl_keys.p, ctx->d_cl_vals.p, nu, &skeys, &svals);
+            ctx->n = keep_n;
+            if (rc) return rc;
+        }
+        asb::asb_cl_strand_kernel<<<grid_for(ctx, nu, 256), 256, 0, ctx->stream>>>(svals, nu, ctx->d_cl_st.p);
+        CU(cudaGetLastError());
+        rc = capped_exact_dev(ctx, skeys, ctx->d_cl_st.p, nu, (int)kmax, ctx->d_cl_out.p, 0);
         if (rc) return rc;
-        asb::asb_cl_assign_kernel<<<grid_for(ctx, nup, 256), 256, 0, ctx->stream>>>(ctx->d_cl_out.p, ctx->d_cl_u.p, nup, na, base, ctx->d_cword.p);
+        asb::asb_cl_assign1_kernel<<<grid_for(ctx, nu, 256), 256, 0, ctx->stream>>>(ctx->d_cl_out.p, skeys, svals, nu, base, ctx->d_cword.p);
         CU(cudaGetLastError());
-        ctx->launches += 3;
+        ctx->launches += 6;
         CU(cudaMemcpyAsync(cword.data(), ctx->d_cword.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         pivots.insert(pivots.end(), acc.begin(), acc.end());
@@ -1199,6 +1307,9 @@ void asb_destroy(asb_ctx* ctx)
     ctx->d_la.release(); ctx->d_lb.release(); ctx->d_lm.release(); ctx->d_bh_pos.release(); ctx->d_bh_key.release(); ctx->d_bh_alt.release();
     ctx->d_bh_alt2.release(); ctx->d_bh_line.release(); ctx->d_bh_first.release();
     ctx->d_qbits.release(); ctx->d_seed_off.release(); ctx->d_order.release(); ctx->d_seeds_f.release(); ctx->d_seeds_r.release(); ctx->d_base2.release();
+    if (ctx->tstream) { cudaStreamSynchronize(ctx->tstream); cudaStreamDestroy(ctx->tstream); }
+    if (ctx->tev) cudaEventDestroy(ctx->tev);
+    if (ctx->h_tctr) cudaFreeHost(ctx->h_tctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1530,11 +1641,11 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
         // One pass appends the pairs the bound leaves for the exact passes.  The probe slab has screen-sized lists
         // (it may still fall back to the screen kernel); later slabs size their lists from the share that survived
         // so far and run again in the rare case that the estimate was too small.
-        uint64_t lcap = ctx->prune_mode == 0 ? std::max<uint64_t>(my_pairs, 32)
-                                             : std::max<uint64_t>(1ull << 20, (uint64_t)((double)my_pairs * ctx->prune_left_ratio * 1.5) + 4096);
+        uint64_t lcap = ctx->prune_mode == 0 ? my_pairs + 32
+                                             : std::min<uint64_t>(my_pairs + 32, std::max<uint64_t>(1ull << 20, (uint64_t)((double)my_pairs * ctx->prune_left_ratio * 1.5) + 4096));
         uint64_t left = 0;
         for (int attempt = 0; attempt < 3; ++attempt) {
-            rc = ensure_lists(ctx, std::min<uint64_t>(lcap, std::max<uint64_t>(my_pairs, 32)));
+            rc = ensure_lists(ctx, lcap);
             if (rc) return rc;
             B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
             B.list_cap = ctx->list_cap;

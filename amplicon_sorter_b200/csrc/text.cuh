@@ -188,30 +188,56 @@ int asb_text_begin(asb_ctx* ctx, const uint32_t* idx_sorted, uint32_t n_pos, con
     return ASB_OK;
 }
 
+// The text stage runs beside the comparison stage: asb_text_load (comparison thread, main stream) stages the records
+// in buffers of its own and records an event; asb_text_step (possibly another host thread) works on a second stream
+// with scratch, counters and pinned scalars of its own, so the lines of slab k are assembled and copied out while
+// asb_batch_step compares slab k + 1.  The caller must not call asb_text_load while an asb_text_step is running.
+static int text_stream(asb_ctx* ctx)
+{
+    if (ctx->tstream) return ASB_OK;
+    CU(cudaStreamCreateWithFlags(&ctx->tstream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->tev, cudaEventDisableTiming));
+    CU(cudaMallocHost(&ctx->h_tctr, sizeof(unsigned long long) * 2));
+    CU(ctx->d_t_err.ensure(1));
+    return ASB_OK;
+}
+
 int asb_text_load(asb_ctx* ctx, const asb_record* dev_recs, uint64_t n, int sort)
 {
-    if (!ctx || (n && !dev_recs)) return fail(ctx, ASB_E_ARG, "null argument");
+    if (!ctx) return ASB_E_ARG;
     CU(cudaSetDevice(ctx->device));
-    ctx->rec_n = 0;
-    if (n == 0) return ASB_OK;
-    CU(ctx->d_t_keys.ensure(n)); CU(ctx->d_t_vals.ensure(n));
-    asb::asb_text_unpack_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(dev_recs, n, ctx->d_t_keys.p, ctx->d_t_vals.p);
-    CU(cudaGetLastError());
-    ctx->launches++;
-    ctx->rec_keys = ctx->d_t_keys.p; ctx->rec_vals = ctx->d_t_vals.p;
-    if (sort && n > 1) {  // per-rank lists are sorted; their union (rows dealt cyclically) is not
-        CU(ctx->d_t_keys_alt.ensure(n)); CU(ctx->d_t_vals_alt.ensure(n));
-        cub::DoubleBuffer<uint64_t> kb(ctx->d_t_keys.p, ctx->d_t_keys_alt.p);
-        cub::DoubleBuffer<uint32_t> vb(ctx->d_t_vals.p, ctx->d_t_vals_alt.p);
-        const int end_bit = std::min(64, 32 + bits_for(ctx->n));
-        size_t tmp = 0;
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
-        CU(ctx->d_tmp.ensure(tmp));
-        CU(cub::DeviceRadixSort::SortPairs(ctx->d_tmp.p, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
-        ctx->rec_keys = kb.Current(); ctx->rec_vals = vb.Current();
+    int rc = text_stream(ctx);
+    if (rc) return rc;
+    ctx->t_rec_n = 0;
+    if (!dev_recs) {  // the sorted records of the last asb_batch_step: the list buffers they live in are reused by the next step
+        n = ctx->rec_n;
+        if (n == 0) return ASB_OK;
+        CU(ctx->d_t_keys.ensure(n)); CU(ctx->d_t_vals.ensure(n));
+        CU(cudaMemcpyAsync(ctx->d_t_keys.p, ctx->rec_keys, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_t_vals.p, ctx->rec_vals, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->t_keys = ctx->d_t_keys.p; ctx->t_vals = ctx->d_t_vals.p;
+    } else {
+        if (n == 0) return ASB_OK;
+        CU(ctx->d_t_keys.ensure(n)); CU(ctx->d_t_vals.ensure(n));
+        asb::asb_text_unpack_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(dev_recs, n, ctx->d_t_keys.p, ctx->d_t_vals.p);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        ctx->t_keys = ctx->d_t_keys.p; ctx->t_vals = ctx->d_t_vals.p;
+        if (sort && n > 1) {  // per-rank lists are sorted; their union (rows dealt cyclically) is not
+            CU(ctx->d_t_keys_alt.ensure(n)); CU(ctx->d_t_vals_alt.ensure(n));
+            cub::DoubleBuffer<uint64_t> kb(ctx->d_t_keys.p, ctx->d_t_keys_alt.p);
+            cub::DoubleBuffer<uint32_t> vb(ctx->d_t_vals.p, ctx->d_t_vals_alt.p);
+            const int end_bit = std::min(64, 32 + bits_for(ctx->n));
+            size_t tmp = 0;
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
+            CU(ctx->d_tmp.ensure(tmp));
+            CU(cub::DeviceRadixSort::SortPairs(ctx->d_tmp.p, tmp, kb, vb, (int64_t)n, 0, end_bit, ctx->stream));
+            ctx->t_keys = kb.Current(); ctx->t_vals = vb.Current();
+        }
     }
-    CU(cudaStreamSynchronize(ctx->stream));  // dev_recs may be released by the caller
-    ctx->rec_n = n;
+    CU(cudaEventRecord(ctx->tev, ctx->stream));
+    if (dev_recs) CU(cudaStreamSynchronize(ctx->stream));  // dev_recs may be released by the caller
+    ctx->t_rec_n = n;
     return ASB_OK;
 }
 
@@ -220,46 +246,46 @@ int asb_text_step(asb_ctx* ctx, uint64_t first, uint64_t count, char* host_dst, 
     if (!ctx || !nbytes) return fail(ctx, ASB_E_ARG, "null argument");
     *nbytes = 0;
     if (!ctx->text_ready) return fail(ctx, ASB_E_ARG, "asb_text_step without asb_text_begin");
-    if (first > ctx->rec_n || count > ctx->rec_n - first) return fail(ctx, ASB_E_ARG, "records [%llu, +%llu) are outside the current %llu records",
-                                                                      (unsigned long long)first, (unsigned long long)count, (unsigned long long)ctx->rec_n);
+    if (first > ctx->t_rec_n || count > ctx->t_rec_n - first) return fail(ctx, ASB_E_ARG, "records [%llu, +%llu) are outside the %llu staged records (asb_text_load)",
+                                                                          (unsigned long long)first, (unsigned long long)count, (unsigned long long)ctx->t_rec_n);
     CU(cudaSetDevice(ctx->device));
     const uint64_t n = count;
     if (n == 0) return ASB_OK;
-    const uint64_t* keys = ctx->rec_keys + first;
-    const uint32_t* vals = ctx->rec_vals + first;
+    cudaStream_t ts = ctx->tstream;
+    CU(cudaStreamWaitEvent(ts, ctx->tev, 0));
+    const uint64_t* keys = ctx->t_keys + first;
+    const uint32_t* vals = ctx->t_vals + first;
     if (ctx->n_lines + n > 0xFFFFFFF0ull) return fail(ctx, ASB_E_ARG, "more than 2^32 lines are not supported");
     const size_t total = (size_t)(ctx->n_lines + n);
-    CU(grow_keep(ctx->d_la, total, ctx->n_lines, ctx->stream)); CU(grow_keep(ctx->d_lb, total, ctx->n_lines, ctx->stream));
-    CU(grow_keep(ctx->d_lm, total, ctx->n_lines, ctx->stream)); CU(grow_keep(ctx->d_lr, total, ctx->n_lines, ctx->stream));
+    CU(grow_keep(ctx->d_la, total, ctx->n_lines, ts)); CU(grow_keep(ctx->d_lb, total, ctx->n_lines, ts));
+    CU(grow_keep(ctx->d_lm, total, ctx->n_lines, ts)); CU(grow_keep(ctx->d_lr, total, ctx->n_lines, ts));
     CU(ctx->d_t_len.ensure(n + 1)); CU(ctx->d_t_off.ensure(n + 1));
     asb::TextTabs T;
     T.idx_sorted = ctx->d_t_idx.p; T.pos_len = ctx->d_pos_len.p; T.lbase = ctx->d_t_lbase.p; T.soff = ctx->d_t_soff.p; T.milli = ctx->d_t_milli.p;
     T.sbuf = reinterpret_cast<const char*>(ctx->d_t_sbuf.p); T.n_pos = ctx->t_n_pos; T.lbase_len = ctx->t_lbase_len; T.n_strings = ctx->t_n_strings;
-    CU(cudaMemsetAsync(ctx->d_ctr.p + asb::C_ERR, 0, sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_t_err.p, 0, sizeof(unsigned long long), ts));
     const size_t l0 = (size_t)ctx->n_lines;
-    asb::asb_text_len_kernel<<<grid_for(ctx, n + 1, 256), 256, 0, ctx->stream>>>(keys, vals, n, T, ctx->d_t_len.p, ctx->d_la.p + l0, ctx->d_lb.p + l0,
-                                                                                  ctx->d_lm.p + l0, ctx->d_lr.p + l0, ctx->d_ctr.p + asb::C_ERR);
+    asb::asb_text_len_kernel<<<grid_for(ctx, n + 1, 256), 256, 0, ts>>>(keys, vals, n, T, ctx->d_t_len.p, ctx->d_la.p + l0, ctx->d_lb.p + l0,
+                                                                      ctx->d_lm.p + l0, ctx->d_lr.p + l0, ctx->d_t_err.p);
     CU(cudaGetLastError());
-    ctx->launches++;
     auto len64 = thrust::make_transform_iterator(static_cast<const uint32_t*>(ctx->d_t_len.p), asb::U32ToU64());
     size_t tmp = 0;
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, len64, ctx->d_t_off.p, (int64_t)n + 1, ctx->stream));
-    CU(ctx->d_tmp.ensure(tmp));
-    CU(cub::DeviceScan::ExclusiveSum(ctx->d_tmp.p, tmp, len64, ctx->d_t_off.p, (int64_t)n + 1, ctx->stream));
-    CU(cudaMemcpyAsync(&ctx->h_ctr[0], ctx->d_t_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&ctx->h_ctr[1], ctx->d_ctr.p + asb::C_ERR, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    const uint64_t bytes = ctx->h_ctr[0];
-    if (ctx->h_ctr[1]) return fail(ctx, ASB_E_ARG, "a record has no entry in the iden string table (asb_text_begin)");
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, len64, ctx->d_t_off.p, (int64_t)n + 1, ts));
+    CU(ctx->d_t_tmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(ctx->d_t_tmp.p, tmp, len64, ctx->d_t_off.p, (int64_t)n + 1, ts));
+    CU(cudaMemcpyAsync(&ctx->h_tctr[0], ctx->d_t_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ts));
+    CU(cudaMemcpyAsync(&ctx->h_tctr[1], ctx->d_t_err.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ts));
+    CU(cudaStreamSynchronize(ts));
+    const uint64_t bytes = ctx->h_tctr[0];
+    if (ctx->h_tctr[1]) return fail(ctx, ASB_E_ARG, "a record has no entry in the iden string table (asb_text_begin)");
     *nbytes = bytes;
     if (bytes > cap || (bytes && !host_dst)) return fail(ctx, ASB_E_NOMEM, "text of %llu bytes does not fit the destination (%llu)", (unsigned long long)bytes, (unsigned long long)cap);
     CU(ctx->d_t_text.ensure(bytes + 16));
-    asb::asb_text_write_kernel<<<(unsigned)((n + asb::kTextBlock - 1) / asb::kTextBlock), asb::kTextBlock, 0, ctx->stream>>>(
+    asb::asb_text_write_kernel<<<(unsigned)((n + asb::kTextBlock - 1) / asb::kTextBlock), asb::kTextBlock, 0, ts>>>(
         keys, vals, n, T, ctx->d_t_off.p, reinterpret_cast<char*>(ctx->d_t_text.p));
     CU(cudaGetLastError());
-    ctx->launches++;
-    CU(cudaMemcpyAsync(host_dst, ctx->d_t_text.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpyAsync(host_dst, ctx->d_t_text.p, bytes, cudaMemcpyDeviceToHost, ts));
+    CU(cudaStreamSynchronize(ts));
     ctx->n_lines += n;
     return ASB_OK;
 }

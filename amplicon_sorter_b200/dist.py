@@ -267,7 +267,7 @@ def _sum_totals(tot, dev):
     import torch
     import torch.distributed as dist
 
-    keys = sorted(k for k, v in tot.items() if isinstance(v, (int, float)))
+    keys = sorted(k for k, v in tot.items() if isinstance(v, (int, float)) and not isinstance(v, bool))
     t = torch.tensor([float(tot[k]) for k in keys], dtype=torch.float64, device=dev)
     dist.all_reduce(t)  # sums; times become rank-sums (reported as such)
     return {k: (int(v) if isinstance(tot[k], int) else float(v)) for k, v in zip(keys, t.tolist())}
@@ -290,34 +290,47 @@ def _run_shard_text(engine, job, dev, r, w, text_tables, sink):
         traceback.print_exc()
         status = 1
     n_rec = 0
-    while True:
-        info, mine = None, None
-        if not status:
-            try:
-                info = engine.batch_step()
-                if info is not None:
-                    mine = engine.step_records_tensor(info["n_records"], dev)
-            except Exception:  # noqa: BLE001
-                import traceback
+    submit, pending = (engine._text_async(sink), None) if r == 0 else (None, None)
+    try:
+        while True:
+            info, mine = None, None
+            if not status:
+                try:
+                    info = engine.batch_step()
+                    if info is not None:
+                        mine = engine.step_records_tensor(info["n_records"], dev)
+                except Exception:  # noqa: BLE001
+                    import traceback
 
-                traceback.print_exc()
-                status = 1
-        merged, done = gather_step(mine, status, info is None, dev)  # raises DistributedAbort on every rank if any failed
-        if done:
-            break
-        for k in TOTALS:
-            tot[k] += info.get(k, 0)
-        tot["steps"] += 1
-        if r == 0 and merged is not None and merged.shape[0]:
-            n_rec += int(merged.shape[0])
-            try:
-                for chunk in engine.text_chunks_tensor(merged, sort=w > 1):
-                    sink(chunk)
-            except Exception:  # noqa: BLE001 -- the next gather_step tells the other ranks
-                import traceback
+                    traceback.print_exc()
+                    status = 1
+            if pending is not None:  # rank 0: the previous slab's text went out while this slab was compared
+                try:
+                    pending.result()
+                except Exception:  # noqa: BLE001 -- gather_step tells the other ranks
+                    import traceback
 
-                traceback.print_exc()
-                status = 1
+                    traceback.print_exc()
+                    status = 1
+                pending = None
+            merged, done = gather_step(mine, status, info is None, dev)  # raises DistributedAbort on every rank if any failed
+            if done:
+                break
+            for k in TOTALS:
+                tot[k] += info.get(k, 0)
+            tot["steps"] += 1
+            if r == 0 and merged is not None and merged.shape[0]:
+                n_rec += int(merged.shape[0])
+                try:
+                    pending = submit(engine.text_load_tensor(merged, sort=w > 1))
+                except Exception:  # noqa: BLE001 -- the next gather_step tells the other ranks
+                    import traceback
+
+                    traceback.print_exc()
+                    status = 1
+    finally:
+        if pending is not None:
+            pending.result()
     tot = _sum_totals(tot, dev)
     tot["n_records"] = n_rec
     return tot

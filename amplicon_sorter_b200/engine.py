@@ -37,24 +37,61 @@ TOTALS = ("pairs", "n_records", "fwd_survivors", "rc_survivors", "zone_checks", 
 
 
 class EngineBase:
-    """What every engine offers on top of batch_begin / batch_step / text_begin / text_step."""
+    """What every engine offers on top of batch_begin / batch_step / text_begin / text_load / text_chunks."""
+
+    _pool = None
+
+    def _text_async(self, sink):
+        """Lines of the staged record set -> sink, on a helper thread (the text stage has its own CUDA stream): the
+        comparison of the next slab runs meanwhile.  Returns a future; wait for it before the next text_load."""
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._pool = ThreadPoolExecutor(1, thread_name_prefix="asb200-text")
+
+        def emit(n):
+            for chunk in self.text_chunks(n):
+                sink(chunk)
+
+        return lambda n: self._pool.submit(emit, n)
 
     def compare_text(self, order, hi, dpass, drev, text_tables, sink, rank=0, world=1):
-        """All steps of one batch, the lines of every step handed to `sink(chunk)` in file order as they are produced
-        (the next slab is compared while a writer thread appends the previous one).  Returns the totals dict."""
+        """All steps of one batch, the lines of every step handed to `sink(chunk)` in file order as they are produced:
+        while slab k + 1 is compared, the text of slab k is assembled on the GPU's second stream, copied out and
+        appended by the writer threads.  Returns the totals dict."""
         self.batch_begin(order, hi, dpass, drev, rank, world)
         self.text_begin(*text_tables)
         tot = dict.fromkeys(TOTALS, 0)
         tot["steps"] = 0
-        while True:
-            info = self.batch_step()
-            if info is None:
-                break
-            for k in TOTALS:
-                tot[k] += info.get(k, 0)
-            tot["steps"] += 1
-            for chunk in self.text_chunks(info["n_records"]):
-                sink(chunk)
+        import time
+
+        submit, pending = self._text_async(sink), None
+        t_step = t_wait = t_load = 0.0
+        try:
+            while True:
+                t0 = time.perf_counter()
+                info = self.batch_step()
+                t1 = time.perf_counter()
+                if pending is not None:
+                    pending.result()  # the previous slab's text is out: its staging buffers are free again
+                    pending = None
+                t2 = time.perf_counter()
+                t_step += t1 - t0
+                t_wait += t2 - t1
+                if info is None:
+                    break
+                for k in TOTALS:
+                    tot[k] += info.get(k, 0)
+                tot["steps"] += 1
+                if info["n_records"]:
+                    self.text_load(None, info["n_records"])
+                    pending = submit(info["n_records"])
+                t_load += time.perf_counter() - t2
+        finally:
+            if pending is not None:
+                pending.result()
+        # host view of the loop: time inside asb_batch_step, time waiting for text that did not overlap, staging
+        tot["host_ms"] = {"batch_step calls": t_step * 1e3, "waiting for the text stage": t_wait * 1e3, "staging records": t_load * 1e3}
         return tot
 
 
@@ -69,7 +106,7 @@ class Engine(EngineBase):
         self.device = device
         self.n_reads = 0
         self._lines_token = None  # groups.upload: the Lines object whose arrays are resident on the device
-        self._slots = [_Slot() for _ in range(3)]  # pinned host buffers of the text ring
+        self._slots = [_Slot() for _ in range(6)]  # pinned host buffers of the text ring (writer threads + one being filled)
         self._slot_next = 0
 
     # -- plumbing ------------------------------------------------------------------------------
@@ -81,6 +118,9 @@ class Engine(EngineBase):
     def close(self):
         if getattr(self, "_h", None):
             self._evict_lines()
+            if self._pool is not None:
+                self._pool.shutdown(wait=True)
+                self._pool = None
             for sl in self._slots:
                 sl.free.wait()
                 if sl.ptr:
@@ -255,9 +295,10 @@ class Engine(EngineBase):
         for first in range(0, int(n_records), _ffi.TEXT_CHUNK):
             yield self.text_step(first, min(_ffi.TEXT_CHUNK, int(n_records) - first))
 
-    def text_load(self, dev_ptr: int, n_records: int, sort: bool = True):
-        """Make n_records asb_records in device memory at dev_ptr the current record set (sorted if asked)."""
-        self._check(self._lib.asb_text_load(self._h, C.c_void_p(dev_ptr), int(n_records), int(bool(sort))))
+    def text_load(self, dev_ptr: int | None, n_records: int, sort: bool = True):
+        """Stage the record set of the text stage: the last step's records (dev_ptr None), or n_records asb_records in
+        device memory at dev_ptr (sorted if asked)."""
+        self._check(self._lib.asb_text_load(self._h, C.c_void_p(dev_ptr) if dev_ptr else None, int(n_records), int(bool(sort))))
 
     def step_records_tensor(self, n_records: int, dev):
         """The last step's records as an (n, 4) int32 tensor on this engine's GPU (for the NCCL gather)."""
@@ -268,12 +309,12 @@ class Engine(EngineBase):
             self.batch_records_dev(t.data_ptr())
         return t
 
-    def text_chunks_tensor(self, recs, sort: bool = True):
-        """Lines of an (n, 4) int32 tensor of records on this engine's GPU (the NCCL gather of several ranks' lists)."""
+    def text_load_tensor(self, recs, sort: bool = True):
+        """Stage an (n, 4) int32 tensor of records on this engine's GPU (the NCCL gather of several ranks' lists)."""
         n = int(recs.shape[0])
         if n:
             self.text_load(recs.data_ptr(), n, sort)
-        return self.text_chunks(n)
+        return n
 
     def lines_hist(self):
         """(hist[1001] of iden*1000 over the resident lines, device ms)."""

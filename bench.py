@@ -342,6 +342,7 @@ def main():
         if flush_buf is not None:
             flush_buf.zero_()  # inputs smaller than L2 (small configs): evict them between timed steps
         tot = job()
+        host_ms = tot.pop("host_ms", None)
         agg = tot if agg is None else {k: agg[k] + tot[k] for k in agg}
     t_res = region.end()
     clocks = sampler.stop()
@@ -423,6 +424,7 @@ def main():
                 "device_time_ms_per_step": {"asb_screen or asb_prune": screen_s * 1e3 / a.steps, "asb_lists": lists_s * 1e3 / a.steps,
                                             "all kernels of the steps (events)": total_s * 1e3 / a.steps,
                                             "pivot selection + read assignment (first step of a job)": agg["cluster_ms"] / world / a.steps},
+                "host_loop_ms_last_step": {k: round(v, 1) for k, v in (host_ms or {}).items()},
                 "word_updates_per_s": wu_rate, "alu_ops_per_word_update": ALU_OPS_PER_WORD_UPDATE,
                 "word_updates_per_pair": agg["word_updates"] / max(agg["pairs"], 1),
                 "useful_word_updates_per_pair": agg["useful_word_updates"] / max(agg["pairs"], 1),

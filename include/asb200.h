@@ -121,9 +121,12 @@ int64_t asb_format_records(const asb_record *recs, uint64_t n, const uint32_t *i
  * asb_text_step turns records [first, first + count) of the CURRENT record set into lines "idxA:idxB:iden[:reverse]\n"
  * in (i_pos, j_pos) order, copies the text to host_dst (cap bytes; pinned memory from asb_host_alloc) and APPENDS the
  * same lines in integer form to the resident line set, so SSG / the best-hit filters run without parsing the file.
- * Call it with consecutive ranges (a writer thread appends one chunk while the next is assembled).  The current
- * record set is the sorted output of the last asb_batch_step, or what asb_text_load staged: n records in DEVICE
- * memory, e.g. the NCCL gather of several ranks' lists; sort != 0 orders them by (i_pos, j_pos) first. */
+ * Call it with consecutive ranges (writer threads append one chunk while the next is assembled).  The current
+ * record set is what asb_text_load staged: dev_recs == NULL -> the sorted output of the last asb_batch_step; else n
+ * records in DEVICE memory, e.g. the NCCL gather of several ranks' lists (sort != 0 orders them by (i_pos, j_pos)).
+ * The text stage has a stream and scratch of its own: asb_text_step may run on a second host thread WHILE
+ * asb_batch_step compares the next slab -- that is the one exception to "a context is not re-entrant"; the caller
+ * must not call asb_text_load before the asb_text_step calls on the previous record set have returned. */
 int asb_text_begin(asb_ctx *ctx, const uint32_t *idx_sorted, uint32_t n_pos, const uint32_t *lbase, uint32_t lbase_len,
                    const uint32_t *soff, const uint16_t *milli, uint32_t n_strings, const char *sbuf, uint32_t sbuf_len);
 int asb_text_load(asb_ctx *ctx, const asb_record *dev_recs, uint64_t n, int sort);

@@ -39,15 +39,20 @@ class OracleEngine(EngineBase):
         self._res = [np.zeros(0, np.uint32)] * 3 + [np.zeros(0, bool)]
         self._lines_token = None
 
-    def text_chunks(self, n_records):
-        return [self._format(self._recs)] if n_records else []
+    def text_load(self, dev_ptr, n_records, sort=True):
+        assert dev_ptr is None
+        self._staged = self._recs
 
-    def text_chunks_tensor(self, recs, sort=True):
+    def text_load_tensor(self, recs, sort=True):
         r = recs.cpu().numpy().view(np.uint32).reshape(-1).view(RECORD)
         if sort:
             key = r["i_pos"].astype(np.uint64) << np.uint64(32) | r["j_pos"].astype(np.uint64)
             r = r[np.argsort(key, kind="stable")]
-        return [self._format(r)] if r.shape[0] else []
+        self._staged = r
+        return int(r.shape[0])
+
+    def text_chunks(self, n_records):
+        return [self._format(self._staged)] if n_records else []
 
     def _format(self, recs):
         idx, lbase, soff, milli, sbuf = self._tabs

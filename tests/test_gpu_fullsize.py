@@ -62,3 +62,56 @@ def test_full_size_config(engine, cfg, row_stride):
     mk = merged["i_pos"].astype(np.uint64) << np.uint64(32) | merged["j_pos"].astype(np.uint64)
     merged = merged[np.argsort(mk, kind="stable")]
     assert checksum(merged) == crc
+
+
+@pytest.mark.parametrize("cfg", [1, 3])
+def test_full_size_batched_configs(engine, cfg):
+    """BASELINE configs 1 and 3 at full size: default mode (one batch of 1,000 + nine empty ones) and -ra (20 overlapping
+    random batches of 1,000 out of 10,000 reads), every batch laid end to end as ONE engine batch
+    (host.AllPairs.plan) -- against the oracle run batch by batch, every pair."""
+    import bench
+    from amplicon_sorter_b200 import host, thresholds
+
+    reads, _, _ = synth.make_config(cfg)
+    buf, offs = synth.pack_reads(reads)
+    lens = (offs[1:] - offs[:-1]).astype(np.int64)
+    batches = [np.asarray(b, dtype=np.int64) for b in bench.batches_of(cfg, len(reads)) if len(b)]
+    ap = host.AllPairs(engine)
+    ap.lens = lens
+    perms, order, lens_sorted, hi, tl = ap.plan(batches)
+    dpass, drev = thresholds.tables(0.80, int(lens.max()) + 1)
+    engine.upload_reads(buf, offs)
+    got, tot = engine.compare_batch(order, hi, dpass, drev)
+    assert tot["pairs"] == tl
+    want, base, pairs = [], 0, 0
+    for b in batches:
+        o = b[np.argsort(lens[b], kind="stable")].astype(np.uint32)
+        recs, st = oracle.process_batch(buf, offs, o, 80.0)
+        recs = recs.copy()
+        recs["i_pos"] += base
+        recs["j_pos"] += base
+        want.append(recs)
+        pairs += st["pairs"]
+        base += len(b)
+    assert pairs == tl and len(batches) == (1 if cfg == 1 else 20)
+    util.assert_same_records(got, np.concatenate(want))
+    # the file host.process_list writes for these batches has the CRC the bench checks
+    text = host.format_records(got, order.astype(np.int64), lens_sorted, dpass)
+    assert zlib.crc32(text.encode()) == bench.KNOWN_TEXT_CRC[cfg]
+
+
+def test_full_size_text_crc_matches_host_formatter(engine):
+    """cfg5 at full size: the device-assembled tempfile (CRC pinned in bench.KNOWN_TEXT_CRC, checked by every bench run
+    at any GPU count) equals the host-side formatter applied to the records -- whose sampled rows the test above
+    compares with the oracle."""
+    import bench
+    from amplicon_sorter_b200 import host
+
+    reads, _, _ = synth.make_config(5)
+    buf, offs, order, lens_sorted, hi, dpass, drev = util.batch_inputs(reads)
+    engine.upload_reads(buf, offs)
+    recs, tot = engine.compare_batch(order, hi, dpass, drev)
+    crc = 0
+    for a in range(0, len(recs), 1 << 21):  # formatted in pieces: 540 MB of text
+        crc = zlib.crc32(host.format_records(recs[a:a + (1 << 21)], order.astype(np.int64), lens_sorted, dpass).encode(), crc)
+    assert crc == bench.KNOWN_TEXT_CRC[5] and len(recs) == 24887125

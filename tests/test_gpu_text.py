@@ -77,7 +77,7 @@ def test_text_step_on_gathered_records_sorts_them(engine):
     allr = np.concatenate(parts[::-1])  # rank order reversed: nothing may depend on it
     t = torch.from_numpy(allr.view(np.uint32).reshape(-1, 4).view(np.int32).copy()).cuda()
     got = b""
-    for chunk in engine.text_chunks_tensor(t, sort=True):
+    for chunk in engine.text_chunks(engine.text_load_tensor(t, sort=True)):
         got += bytes(chunk.data)
         chunk.release()
     want, _, _ = oracle_text(reads, np.arange(len(reads)))
@@ -97,6 +97,7 @@ def test_text_errors_are_reported(engine):
     engine.text_begin(*host.text_tables(order, lens_sorted, short))
     info = engine.batch_step()
     assert info["n_records"] > 0
+    engine.text_load(None, info["n_records"])
     with pytest.raises(EngineError):
         engine.text_step(0, info["n_records"])
     with pytest.raises(EngineError):  # a range outside the current record set
