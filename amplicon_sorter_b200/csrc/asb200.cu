@@ -973,21 +973,6 @@ __global__ void __launch_bounds__(256) asb_cl_gen_kernel(const uint32_t* __restr
     }
 }
 
-// per uncovered read: the closest of the np new pivots (either orientation) within the cap -> its cluster word
-__global__ void __launch_bounds__(256) asb_cl_assign_kernel(const int32_t* __restrict__ out, const uint32_t* __restrict__ reads, uint32_t nu, uint32_t np,
-                                                          uint32_t piv_base, uint32_t* __restrict__ cword)
-{
-    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
-        uint32_t best = kUncovered;
-        int bd = 0x7FFFFFFF;
-        for (uint32_t ps = 0; ps < 2 * np; ++ps) {
-            const int d = out[(uint64_t)ps * nu + u];
-            if (d >= 0 && d < bd) { bd = d; best = ((piv_base + (ps >> 1)) << 20) | ((ps & 1u) << 19) | (uint32_t)d; }
-        }
-        if (best != kUncovered) cword[reads[u]] = best;
-    }
-}
-
 // int32 capped distances ((p * 2 + x) * m + q) -> u16 lower bounds, "more than the cap" = cap + 1
 __global__ void __launch_bounds__(256) asb_cl_matrix_kernel(const int32_t* __restrict__ out, uint64_t total, uint32_t cap, uint16_t* __restrict__ D)
 {
@@ -1114,25 +1099,6 @@ int capped_exact_dev(asb_ctx* ctx, const uint64_t* d_keys, const uint8_t* d_st, 
     int rc = run_list(ctx, B, M_EXACT, cls, const_cast<uint64_t*>(d_keys), nullptr, n_entries);
     if (rc) return rc;
     return read_counters(ctx);
-}
-
-// Window words of one warp whose 32 targets have lengths n_lo..n_hi against a query of length m at threshold cap
-// (process_group's geometry: D = e + max(n - m, 0), E = e + max(m - n, 0), e = (k - |n - m|) / 2, lanes with |n - m| > k idle).
-int slice_need(int m, int n_lo, int n_hi, int cap)
-{
-    int Dmax = 0, Emax = 0;
-    const int pts[3] = {n_lo, n_hi, std::min(std::max(m, n_lo), n_hi)};
-    for (int x = 0; x < 3; ++x) {
-        // the extremes of D and E over [n_lo, n_hi] sit at its ends, at n = m, or where a lane drops out (|n - m| = k)
-        for (int n : {pts[x], std::min(std::max(m - cap, n_lo), n_hi), std::min(std::max(m + cap, n_lo), n_hi)}) {
-            const int k = std::min(std::max(n, m), cap), dl = std::abs(n - m);
-            if (dl > k) continue;
-            const int e = (k - dl) >> 1;
-            Dmax = std::max(Dmax, e + std::max(n - m, 0));
-            Emax = std::max(Emax, e + std::max(m - n, 0));
-        }
-    }
-    return ((Dmax + 31) >> 5) + ((Emax + 31) >> 5) + 1;
 }
 
 // Picks pivot reads and assigns every read it can to a pivot (see asb_prune).  Deterministic: same reads, same kmax
@@ -1804,8 +1770,7 @@ int asb_kmer_build(asb_ctx* ctx, int k)
     CU(ctx->d_roff_all.ensure((size_t)n + 1)); CU(ctx->d_rlen_all.ensure(std::max<uint32_t>(n, 1)));
     uint8_t base2[256];
     fill_base2(ctx, base2);
-    DevBuf<uint8_t> d_b2;
-    struct Guard { DevBuf<uint8_t>& a; ~Guard() { a.release(); } } guard{d_b2};
+    DevBuf<uint8_t>& d_b2 = ctx->d_base2;  // resident (the seed tables use the same map)
     CU(d_b2.ensure(256));
     CU(cudaMemcpyAsync(d_b2.p, base2, 256, cudaMemcpyHostToDevice, ctx->stream));
     if (n) {
@@ -1827,8 +1792,7 @@ int asb_kmer_shared_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, ui
     if (n == 0) return ASB_OK;
     for (uint64_t p = 0; p < n; ++p) if (a[p] >= ctx->n_reads || b[p] >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "pair %llu: bad read id", (unsigned long long)p);
     CU(cudaSetDevice(ctx->device));
-    DevBuf<uint32_t> da, db, dout;
-    struct Guard { DevBuf<uint32_t>&a,&b,&c; ~Guard() { a.release(); b.release(); c.release(); } } guard{da, db, dout};
+    DevBuf<uint32_t>& da = ctx->d_s_u32[0]; DevBuf<uint32_t>& db = ctx->d_s_u32[1]; DevBuf<uint32_t>& dout = ctx->d_s_u32[2];  // resident scratch
     CU(da.ensure(n)); CU(db.ensure(n)); CU(dout.ensure(n));
     CU(cudaMemcpyAsync(da.p, a, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(db.p, b, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -1848,8 +1812,7 @@ int asb_kmer_shared_tile(asb_ctx* ctx, const uint32_t* rows, uint32_t nr, const 
     for (uint32_t i = 0; i < nr; ++i) if (rows[i] >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "rows[%u]: bad read id", i);
     for (uint32_t i = 0; i < nc; ++i) if (cols[i] >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "cols[%u]: bad read id", i);
     CU(cudaSetDevice(ctx->device));
-    DevBuf<uint32_t> dr, dc, dout;
-    struct Guard { DevBuf<uint32_t>&a,&b,&c; ~Guard() { a.release(); b.release(); c.release(); } } guard{dr, dc, dout};
+    DevBuf<uint32_t>& dr = ctx->d_s_u32[0]; DevBuf<uint32_t>& dc = ctx->d_s_u32[1]; DevBuf<uint32_t>& dout = ctx->d_s_u32[2];  // resident scratch
     CU(dr.ensure(nr)); CU(dc.ensure(nc)); CU(dout.ensure((size_t)nr * nc));
     CU(cudaMemcpyAsync(dr.p, rows, sizeof(uint32_t) * nr, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(dc.p, cols, sizeof(uint32_t) * nc, cudaMemcpyHostToDevice, ctx->stream));
@@ -1949,8 +1912,7 @@ int asb_distance_pairs(asb_ctx* ctx, const uint32_t* a, const uint32_t* b, const
     CU(ctx->d_pos_off.ensure(n)); CU(ctx->d_pos_len.ensure(n));
     CU(cudaMemcpyAsync(ctx->d_pos_off.p, ctx->h_roff.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_pos_len.p, ctx->h_rlen.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-    DevBuf<uint64_t> d_keys; DevBuf<uint8_t> d_st; DevBuf<int32_t> d_out;
-    struct Guard { DevBuf<uint64_t>&a; DevBuf<uint8_t>&b; DevBuf<int32_t>&c; ~Guard(){a.release();b.release();c.release();} } guard{d_keys, d_st, d_out};
+    DevBuf<uint64_t>& d_keys = ctx->d_cl_keys; DevBuf<uint8_t>& d_st = ctx->d_cl_st; DevBuf<int32_t>& d_out = ctx->d_cl_out;  // resident scratch
     CU(d_keys.ensure(npairs)); CU(d_st.ensure(npairs)); CU(d_out.ensure(npairs));
     CU(cudaMemcpyAsync(d_keys.p, keys.data(), sizeof(uint64_t) * npairs, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(d_st.p, st.data(), npairs, cudaMemcpyHostToDevice, ctx->stream));

@@ -148,20 +148,36 @@ template <int LEN, int NB>
 __device__ __forceinline__ void cols32_fast(uint32_t (&Pv)[NB], uint32_t (&Mv)[NB], const uint32_t* __restrict__ peqb,
                                             const int Wpad, const uint32_t* __restrict__ tgt32, uint32_t& nxt)
 {
-    // two columns per iteration: the union of all LEN variants must stay inside the instruction
-    // cache (a 4-column unroll of 9 variants thrashed it: ncu stall_no_instruction = 15 per issue)
+    // The union of all LEN variants a kernel can be in at the same time must stay inside the instruction cache.
+    // Narrow windows: two columns per iteration (a 4-column unroll of 9 variants thrashed it: ncu stall_no_instruction
+    // = 15 per issue).  Wide windows (LEN >= 10: the zone pass and long reads): one column per iteration -- the loop
+    // overhead is 3 instructions against >= 120, and the two-column bodies of the 20-word class measured
+    // stall_no_instruction = 6.0 per issue (profiles/r2_asb_lists_ncu_full.txt).
     uint32_t cw = 0;
+    if constexpr (LEN >= 10) {
 #pragma unroll 1
-    for (int q = 0; q < 16; ++q) {
-        if ((q & 1) == 0) { cw = nxt; nxt = __ldg(tgt32 + (q >> 1) + 1); }
-        else cw >>= 16;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const uint32_t sym = __byte_perm(cw, 0u, 0x4440u + s);
+        for (int q = 0; q < 32; ++q) {
+            if ((q & 3) == 0) { cw = nxt; nxt = __ldg(tgt32 + (q >> 2) + 1); }
+            else cw >>= 8;
+            const uint32_t sym = cw & 0xFFu;
             const uint32_t* __restrict__ row = peqb + sym * Wpad;
             uint32_t php = 0x80000000u, mhp = 0u, hmb = 0u;  // hin = +1 above the first active word
 #pragma unroll
             for (int t = 0; t < LEN; ++t) ASB_WORD_UPDATE(row[t], Pv[t], Mv[t], php, mhp, hmb)
+        }
+    } else {
+#pragma unroll 1
+        for (int q = 0; q < 16; ++q) {
+            if ((q & 1) == 0) { cw = nxt; nxt = __ldg(tgt32 + (q >> 1) + 1); }
+            else cw >>= 16;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const uint32_t sym = __byte_perm(cw, 0u, 0x4440u + s);
+                const uint32_t* __restrict__ row = peqb + sym * Wpad;
+                uint32_t php = 0x80000000u, mhp = 0u, hmb = 0u;  // hin = +1 above the first active word
+#pragma unroll
+                for (int t = 0; t < LEN; ++t) ASB_WORD_UPDATE(row[t], Pv[t], Mv[t], php, mhp, hmb)
+            }
         }
     }
 }
@@ -271,7 +287,7 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
             for (int q = 0; q < 8; ++q) {
                 const uint32_t cw = nxt;
                 nxt = __ldg(tgt32 + cb * 8 + q + 1);
-#pragma unroll
+#pragma unroll(BT > 0 && BT <= 9 ? 4 : 1)
                 for (int s = 0; s < 4; ++s) {
                     const uint32_t sym = (cw >> (8 * s)) & 0xFFu;
                     const uint32_t* __restrict__ row = peqb + sym * Wpad;
