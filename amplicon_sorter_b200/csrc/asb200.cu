@@ -1531,7 +1531,9 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     }
     const bool try_prune = ctx->prune_mode >= 0;
     // slab: rows of one window class, at most pair_cap pairs (once pruning is known to work: 2^30, few pairs survive)
-    const uint64_t slab_cap = ctx->prune_mode == 1 ? std::max<uint64_t>(ctx->pair_cap, 1ull << 30) : ctx->pair_cap;
+    // (2^30 pairs per slab over ALL ranks: with more ranks the slabs must not become fewer, or nothing is left to overlap
+    // the gather and the text of a slab with)
+    const uint64_t slab_cap = ctx->prune_mode == 1 ? std::max<uint64_t>(ctx->pair_cap, (1ull << 30) / ctx->world) : ctx->pair_cap;
     const int cls = class_for(std::min(need_words(ctx, r0, ctx->h_pmax_dpass, 0), (int)((ctx->h_len[r0] + 31) / 32)));
     // Rows are dealt to the ranks cyclically (row p belongs to rank p % world): a rank then sees whole rows, so the
     // row-runs of its sorted lists are as long as on a single GPU (dealing 32-target groups instead left 1/world of

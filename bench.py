@@ -63,6 +63,7 @@ DESCR = {
     3: "cfg3: -ra, 20 random batches of 1,000 from a 10,000-read 50-species mix (~700 bp)",
     4: "cfg4: --all on 50,000 synthetic reads, 10 loci as full (~1 kb) and nested (~870 bp) amplicons",
     5: "cfg5: --all on 100,000 synthetic ~1 kb reads (200 templates, 6% ONT-like error, both strands, 1% with N)",
+    6: "cfg6 (not a BASELINE config): cfg5's shape with RELATED templates, 20 ancestors x 10 siblings at 8-15% from the ancestor",
 }
 
 
@@ -277,7 +278,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5], help="BASELINE.json config (default 5, the headline)")
+    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5, 6],
+                    help="BASELINE.json config (default 5, the headline); 6 = config 5 with related templates (worst case for the pivot bound)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the config's read count (debugging)")
     ap.add_argument("--reads", type=int, default=0, help="shorthand for --scale on config 5")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)

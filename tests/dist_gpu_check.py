@@ -18,11 +18,40 @@ from oracle import oracle  # noqa: E402
 from tests import util  # noqa: E402
 
 
+def failing(r, w, dev, eng):
+    """--fail: the engine of the LAST rank fails inside its first batch_step; every rank must leave through
+    DistributedAbort (no rank parked in an NCCL collective), and say so."""
+    from amplicon_sorter_b200._ffi import EngineError
+
+    if r == w - 1:
+        def boom():
+            raise EngineError(-1, "injected: CUDA error in batch_step")
+        eng.batch_step = boom
+    reads, _, _ = synth.make_config(5, scale=0.01)
+    try:
+        if r != 0:
+            dist.worker_loop(eng, dev)
+        else:
+            sh = dist.ShardedEngine(eng, dev)
+            with tempfile.TemporaryDirectory() as tmp:
+                args = types.SimpleNamespace(outputfolder=tmp, similar_genes=80.0)
+                try:
+                    host.process_list([[[f"r{i}", s.decode(), "u", i] for i, s in enumerate(reads)]], "x_compare.tmp", args, engine=sh)
+                except Exception:  # the reference's per-file handler must not see the abort
+                    print("SWALLOWED", flush=True)
+        print(f"rank {r}: returned normally", flush=True)
+    except dist.DistributedAbort as exc:
+        print(f"rank {r}: aborted: {exc}", flush=True)
+        os._exit(3)
+
+
 def main():
     r, w, dev = dist.init_from_env()
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     eng = Engine(dev.index, stream=stream.cuda_stream)
+    if "--fail" in sys.argv:
+        return failing(r, w, dev, eng)
     if r != 0:
         dist.worker_loop(eng, dev)
         return

@@ -133,3 +133,16 @@ def test_torchrun_sharded_engine_matches_oracle(world, tmp_path):
                           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("identical to the oracle") >= 3, out.stdout
+
+
+def test_torchrun_engine_failure_aborts_every_rank(tmp_path):
+    """Real NCCL: an engine error on one rank stops all ranks at the same step -- no hang, no swallowed exception."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    port = 29750 + os.getpid() % 200
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), os.path.join(ROOT, "tests", "dist_gpu_check.py"), "--fail"], capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0
+    assert out.stdout.count("aborted:") == 2 and "SWALLOWED" not in out.stdout and "returned normally" not in out.stdout, out.stdout + out.stderr[-2000:]
