@@ -141,6 +141,13 @@ __device__ __forceinline__ uint32_t asb_add(uint32_t a, uint32_t b) { uint32_t r
 #ifndef ASB_STEP_WIDE
 #define ASB_STEP_WIDE 4
 #endif
+#ifndef ASB_ONECOL_MIN
+#define ASB_ONECOL_MIN 10  // straight-line variants of at least this many words run one column per loop iteration
+#endif
+#ifndef ASB_GENERIC_UNROLL_NARROW
+#define ASB_GENERIC_UNROLL_NARROW 1  // general path (last block of a lane): 4 = unroll the columns of a target word.  Measured on the
+#endif                               // config-5 list passes: 1 -> 312 ms, 4 -> 330 ms per job (instruction cache); screen path unchanged
+
 __host__ __device__ constexpr int len_step(int BT) { return BT <= 9 ? 1 : (BT <= 17 ? 2 : ASB_STEP_WIDE); }
 
 // 32 columns over the first LEN words of the window, straight-line (no per-word control flow).
@@ -154,7 +161,7 @@ __device__ __forceinline__ void cols32_fast(uint32_t (&Pv)[NB], uint32_t (&Mv)[N
     // overhead is 3 instructions against >= 120, and the two-column bodies of the 20-word class measured
     // stall_no_instruction = 6.0 per issue (profiles/r2_asb_lists_ncu_full.txt).
     uint32_t cw = 0;
-    if constexpr (LEN >= 10) {
+    if constexpr (LEN >= ASB_ONECOL_MIN) {
 #pragma unroll 1
         for (int q = 0; q < 32; ++q) {
             if ((q & 3) == 0) { cw = nxt; nxt = __ldg(tgt32 + (q >> 2) + 1); }
@@ -242,6 +249,7 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
 {
     constexpr int NB = BT > 0 ? BT : kMaxDynWords;
     constexpr int STEP = len_step(BT);
+    constexpr int kGenUnroll = (BT > 0 && BT <= 9) ? ASB_GENERIC_UNROLL_NARROW : 1;  // columns of a target word unrolled in the general path
     const int Bmax = BT > 0 ? BT : g.Bw;
     uint32_t Pv[NB], Mv[NB];
     const int wm = (m - 1) >> 5;  // word holding row m
@@ -287,7 +295,7 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
             for (int q = 0; q < 8; ++q) {
                 const uint32_t cw = nxt;
                 nxt = __ldg(tgt32 + cb * 8 + q + 1);
-#pragma unroll(BT > 0 && BT <= 9 ? 4 : 1)
+#pragma unroll kGenUnroll
                 for (int s = 0; s < 4; ++s) {
                     const uint32_t sym = (cw >> (8 * s)) & 0xFFu;
                     const uint32_t* __restrict__ row = peqb + sym * Wpad;
