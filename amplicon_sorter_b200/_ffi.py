@@ -40,7 +40,7 @@ SYMBOLS = ["asb_version", "asb_create", "asb_destroy", "asb_last_error", "asb_se
            "asb_batch_begin", "asb_batch_step", "asb_batch_records", "asb_distance_pairs", "asb_debug_read", "asb_batch_records_dev", "asb_int_peak", "asb_format_records",
            "asb_kmer_build", "asb_kmer_shared_pairs", "asb_kmer_shared_tile", "asb_threeway_pairs",
            "asb_lines_upload", "asb_lines_hist", "asb_lines_besthit", "asb_lines_besthit_fetch", "asb_components",
-           "asb_text_begin", "asb_text_load", "asb_text_step", "asb_host_alloc", "asb_host_free", "asb_lines_count", "asb_lines_fetch"]
+           "asb_text_begin", "asb_text_load", "asb_text_step", "asb_text_measure", "asb_lines_append_dev", "asb_host_alloc", "asb_host_free", "asb_lines_count", "asb_lines_fetch"]
 
 
 def lib_path() -> str:
@@ -89,7 +89,9 @@ def load():
     u16p = C.POINTER(C.c_uint16)
     L.asb_text_begin.argtypes = [vp, u32p, C.c_uint32, u32p, C.c_uint32, u32p, u16p, C.c_uint32, C.c_char_p, C.c_uint32]
     L.asb_text_load.argtypes = [vp, vp, C.c_uint64, C.c_int]
-    L.asb_text_step.argtypes = [vp, C.c_uint64, C.c_uint64, vp, C.c_uint64, u64p]
+    L.asb_text_step.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int, vp, C.c_uint64, u64p]
+    L.asb_text_measure.argtypes = [vp, u64p]
+    L.asb_lines_append_dev.argtypes = [vp, vp, C.c_uint64]
     L.asb_host_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
     L.asb_host_free.argtypes = [vp]
     L.asb_host_free.restype = None

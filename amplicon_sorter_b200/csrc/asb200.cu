@@ -759,7 +759,7 @@ struct asb_ctx {
     uint32_t t_n_pos = 0, t_lbase_len = 0, t_n_strings = 0;
     bool text_ready = false, lines_have_rev = false;
     cudaStream_t tstream = nullptr; cudaEvent_t tev = nullptr; unsigned long long* h_tctr = nullptr;  // the text stage's own stream (text.cuh)
-    DevBuf<uint8_t> d_t_tmp; DevBuf<unsigned long long> d_t_err;
+    DevBuf<uint8_t> d_t_tmp, d_t_sr; DevBuf<unsigned long long> d_t_err; DevBuf<uint32_t> d_t_sa, d_t_sb, d_t_sm;  // + scratch of a text pass that does not append lines
     const uint64_t* t_keys = nullptr; const uint32_t* t_vals = nullptr; uint64_t t_rec_n = 0;  // records staged by asb_text_load
     // cluster pruning (ensure_clusters): per-read cluster words, pivot x pivot lower bounds, and what the batch decided
     DevBuf<uint32_t> d_cword, d_cl_u, d_cl_piv, d_cl_best, d_cl_pb, d_cl_vals; DevBuf<uint16_t> d_pivD; DevBuf<uint64_t> d_cl_keys; DevBuf<uint8_t> d_cl_st; DevBuf<int32_t> d_cl_out;
@@ -1535,15 +1535,15 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     // the gather and the text of a slab with)
     const uint64_t slab_cap = ctx->prune_mode == 1 ? std::max<uint64_t>(ctx->pair_cap, (1ull << 30) / ctx->world) : ctx->pair_cap;
     const int cls = class_for(std::min(need_words(ctx, r0, ctx->h_pmax_dpass, 0), (int)((ctx->h_len[r0] + 31) / 32)));
-    // Rows are dealt to the ranks cyclically (row p belongs to rank p % world): a rank then sees whole rows, so the
-    // row-runs of its sorted lists are as long as on a single GPU (dealing 32-target groups instead left 1/world of
-    // every row on each rank and the list warps mostly empty at 8 GPUs).  Neighbouring rows have almost the same
-    // number of partners, so the shares differ by O(n) pairs of O(n^2 / world).
+    // Every slab's rows are split into `world` CONTIGUOUS ranges of (almost) equal pair counts, rank k takes the k-th:
+    // a rank sees whole rows (long row-runs in its sorted lists), and its records are one contiguous piece of the
+    // slab's lines -- so every rank can print its own piece of the tempfile and write it at its own offset
+    // (dist.py), instead of rank 0 merging, printing and writing everything.  Row p of a slab with `pairs` pairs
+    // and `before` pairs in earlier rows belongs to rank floor(before * world / pairs).
     uint64_t pairs = 0, my_pairs = 0;
     uint32_t r1 = r0;
     int zneed = 0;
     uint32_t wmax = 1;
-    std::vector<uint32_t> my_rows;
     while (r1 < n) {
         const uint64_t cnt = ctx->h_hi[r1] - r1;
         if (cnt) {
@@ -1553,10 +1553,21 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
             if (r1 > r0 && pairs + cnt > slab_cap * ctx->world) break;  // the cap is per rank
             zneed = std::max(zneed, std::min(need_words(ctx, r1, ctx->h_pmax_drev, 1), W));
             wmax = std::max<uint32_t>(wmax, (uint32_t)W);
-            if (r1 % ctx->world == ctx->rank) { my_rows.push_back(r1); my_pairs += cnt; }
         }
         pairs += cnt;
         ++r1;
+    }
+    std::vector<uint32_t> my_rows;
+    {
+        uint64_t before = 0;
+        for (uint32_t r = r0; r < r1; ++r) {
+            const uint64_t cnt = ctx->h_hi[r] - r;
+            if (cnt) {
+                const uint64_t owner = std::min<uint64_t>(ctx->world - 1, (uint64_t)((unsigned __int128)before * ctx->world / std::max<uint64_t>(pairs, 1)));
+                if (owner == ctx->rank) { my_rows.push_back(r); my_pairs += cnt; }
+            }
+            before += cnt;
+        }
     }
     // task space: blocks of kRowBlock of this rank's rows, group-major inside a block (block b holds
     // rows x max groups task slots; a slot past the end of a shorter row is skipped by the kernel)

@@ -126,6 +126,25 @@ __global__ void __launch_bounds__(kTextBlock) asb_text_write_kernel(const uint64
     }
 }
 
+// integer form of the lines of n records (file order) -> la/lb/lm/lr
+__global__ void __launch_bounds__(256) asb_lines_from_records_kernel(const asb_record* __restrict__ recs, uint64_t n, const TextTabs T, uint32_t* __restrict__ la,
+                                                                   uint32_t* __restrict__ lb, uint32_t* __restrict__ lm, uint8_t* __restrict__ lr,
+                                                                   unsigned long long* __restrict__ err)
+{
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+        const asb_record x = recs[r];
+        uint32_t a = 0u, b = 0u, m = 0u;
+        bool ok = x.i_pos < T.n_pos && x.j_pos < T.n_pos;
+        if (ok) {
+            const uint32_t L = T.pos_len[x.j_pos];
+            ok = L < T.lbase_len && T.lbase[L] != 0xFFFFFFFFu && T.lbase[L] + x.d < T.n_strings;
+            if (ok) { a = T.idx_sorted[x.i_pos]; b = T.idx_sorted[x.j_pos]; m = T.milli[T.lbase[L] + x.d]; }
+        }
+        if (!ok) atomicOr(err, (unsigned long long)E_TABLE);
+        la[r] = a; lb[r] = b; lm[r] = m; lr[r] = (uint8_t)(x.reverse & 1u);
+    }
+}
+
 struct U32ToU64 { __host__ __device__ __forceinline__ uint64_t operator()(const uint32_t& x) const { return (uint64_t)x; } };
 
 }  // namespace asb
@@ -241,7 +260,7 @@ int asb_text_load(asb_ctx* ctx, const asb_record* dev_recs, uint64_t n, int sort
     return ASB_OK;
 }
 
-int asb_text_step(asb_ctx* ctx, uint64_t first, uint64_t count, char* host_dst, uint64_t cap, uint64_t* nbytes)
+int asb_text_step(asb_ctx* ctx, uint64_t first, uint64_t count, int append_lines, char* host_dst, uint64_t cap, uint64_t* nbytes)
 {
     if (!ctx || !nbytes) return fail(ctx, ASB_E_ARG, "null argument");
     *nbytes = 0;
@@ -255,18 +274,24 @@ int asb_text_step(asb_ctx* ctx, uint64_t first, uint64_t count, char* host_dst, 
     CU(cudaStreamWaitEvent(ts, ctx->tev, 0));
     const uint64_t* keys = ctx->t_keys + first;
     const uint32_t* vals = ctx->t_vals + first;
-    if (ctx->n_lines + n > 0xFFFFFFF0ull) return fail(ctx, ASB_E_ARG, "more than 2^32 lines are not supported");
-    const size_t total = (size_t)(ctx->n_lines + n);
-    CU(grow_keep(ctx->d_la, total, ctx->n_lines, ts)); CU(grow_keep(ctx->d_lb, total, ctx->n_lines, ts));
-    CU(grow_keep(ctx->d_lm, total, ctx->n_lines, ts)); CU(grow_keep(ctx->d_lr, total, ctx->n_lines, ts));
+    uint32_t *la, *lb, *lm; uint8_t* lr;
+    if (append_lines) {
+        if (ctx->n_lines + n > 0xFFFFFFF0ull) return fail(ctx, ASB_E_ARG, "more than 2^32 lines are not supported");
+        const size_t total = (size_t)(ctx->n_lines + n);
+        CU(grow_keep(ctx->d_la, total, ctx->n_lines, ts)); CU(grow_keep(ctx->d_lb, total, ctx->n_lines, ts));
+        CU(grow_keep(ctx->d_lm, total, ctx->n_lines, ts)); CU(grow_keep(ctx->d_lr, total, ctx->n_lines, ts));
+        const size_t l0 = (size_t)ctx->n_lines;
+        la = ctx->d_la.p + l0; lb = ctx->d_lb.p + l0; lm = ctx->d_lm.p + l0; lr = ctx->d_lr.p + l0;
+    } else {  // the lines of this piece reach the resident set another way (asb_lines_append_dev): scratch
+        CU(ctx->d_t_sa.ensure(n)); CU(ctx->d_t_sb.ensure(n)); CU(ctx->d_t_sm.ensure(n)); CU(ctx->d_t_sr.ensure(n));
+        la = ctx->d_t_sa.p; lb = ctx->d_t_sb.p; lm = ctx->d_t_sm.p; lr = ctx->d_t_sr.p;
+    }
     CU(ctx->d_t_len.ensure(n + 1)); CU(ctx->d_t_off.ensure(n + 1));
     asb::TextTabs T;
     T.idx_sorted = ctx->d_t_idx.p; T.pos_len = ctx->d_pos_len.p; T.lbase = ctx->d_t_lbase.p; T.soff = ctx->d_t_soff.p; T.milli = ctx->d_t_milli.p;
     T.sbuf = reinterpret_cast<const char*>(ctx->d_t_sbuf.p); T.n_pos = ctx->t_n_pos; T.lbase_len = ctx->t_lbase_len; T.n_strings = ctx->t_n_strings;
     CU(cudaMemsetAsync(ctx->d_t_err.p, 0, sizeof(unsigned long long), ts));
-    const size_t l0 = (size_t)ctx->n_lines;
-    asb::asb_text_len_kernel<<<grid_for(ctx, n + 1, 256), 256, 0, ts>>>(keys, vals, n, T, ctx->d_t_len.p, ctx->d_la.p + l0, ctx->d_lb.p + l0,
-                                                                      ctx->d_lm.p + l0, ctx->d_lr.p + l0, ctx->d_t_err.p);
+    asb::asb_text_len_kernel<<<grid_for(ctx, n + 1, 256), 256, 0, ts>>>(keys, vals, n, T, ctx->d_t_len.p, la, lb, lm, lr, ctx->d_t_err.p);
     CU(cudaGetLastError());
     auto len64 = thrust::make_transform_iterator(static_cast<const uint32_t*>(ctx->d_t_len.p), asb::U32ToU64());
     size_t tmp = 0;
@@ -286,6 +311,65 @@ int asb_text_step(asb_ctx* ctx, uint64_t first, uint64_t count, char* host_dst, 
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(host_dst, ctx->d_t_text.p, bytes, cudaMemcpyDeviceToHost, ts));
     CU(cudaStreamSynchronize(ts));
+    if (append_lines) ctx->n_lines += n;
+    return ASB_OK;
+}
+
+// Bytes the staged record set will print to (asb_text_load, then this, then asb_text_step): lets every rank of a
+// multi-GPU run learn the file offset of its piece before anything is written.  Runs on the caller's (main) stream.
+int asb_text_measure(asb_ctx* ctx, uint64_t* nbytes)
+{
+    if (!ctx || !nbytes) return fail(ctx, ASB_E_ARG, "null argument");
+    *nbytes = 0;
+    if (!ctx->text_ready) return fail(ctx, ASB_E_ARG, "asb_text_measure without asb_text_begin");
+    const uint64_t n = ctx->t_rec_n;
+    if (n == 0) return ASB_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(ctx->d_t_sa.ensure(n)); CU(ctx->d_t_sb.ensure(n)); CU(ctx->d_t_sm.ensure(n)); CU(ctx->d_t_sr.ensure(n));
+    CU(ctx->d_t_len.ensure(n + 1)); CU(ctx->d_t_off.ensure(n + 1));
+    asb::TextTabs T;
+    T.idx_sorted = ctx->d_t_idx.p; T.pos_len = ctx->d_pos_len.p; T.lbase = ctx->d_t_lbase.p; T.soff = ctx->d_t_soff.p; T.milli = ctx->d_t_milli.p;
+    T.sbuf = reinterpret_cast<const char*>(ctx->d_t_sbuf.p); T.n_pos = ctx->t_n_pos; T.lbase_len = ctx->t_lbase_len; T.n_strings = ctx->t_n_strings;
+    CU(cudaMemsetAsync(ctx->d_t_err.p, 0, sizeof(unsigned long long), ctx->stream));
+    asb::asb_text_len_kernel<<<grid_for(ctx, n + 1, 256), 256, 0, ctx->stream>>>(ctx->t_keys, ctx->t_vals, n, T, ctx->d_t_len.p, ctx->d_t_sa.p, ctx->d_t_sb.p,
+                                                                                  ctx->d_t_sm.p, ctx->d_t_sr.p, ctx->d_t_err.p);
+    CU(cudaGetLastError());
+    auto len64 = thrust::make_transform_iterator(static_cast<const uint32_t*>(ctx->d_t_len.p), asb::U32ToU64());
+    size_t tmp = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, len64, ctx->d_t_off.p, (int64_t)n + 1, ctx->stream));
+    CU(ctx->d_tmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(ctx->d_tmp.p, tmp, len64, ctx->d_t_off.p, (int64_t)n + 1, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->h_tctr[0], ctx->d_t_off.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&ctx->h_tctr[1], ctx->d_t_err.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_tctr[1]) return fail(ctx, ASB_E_ARG, "a record has no entry in the iden string table (asb_text_begin)");
+    *nbytes = ctx->h_tctr[0];
+    return ASB_OK;
+}
+
+// Appends n records in DEVICE memory (already in file order: the ranks' pieces of a slab, concatenated in rank order)
+// to the resident line set in integer form, without printing them.
+int asb_lines_append_dev(asb_ctx* ctx, const asb_record* dev_recs, uint64_t n)
+{
+    if (!ctx || (n && !dev_recs)) return fail(ctx, ASB_E_ARG, "null argument");
+    if (!ctx->text_ready) return fail(ctx, ASB_E_ARG, "asb_lines_append_dev without asb_text_begin");
+    if (n == 0) return ASB_OK;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->n_lines + n > 0xFFFFFFF0ull) return fail(ctx, ASB_E_ARG, "more than 2^32 lines are not supported");
+    const size_t total = (size_t)(ctx->n_lines + n), l0 = (size_t)ctx->n_lines;
+    CU(grow_keep(ctx->d_la, total, l0, ctx->stream)); CU(grow_keep(ctx->d_lb, total, l0, ctx->stream));
+    CU(grow_keep(ctx->d_lm, total, l0, ctx->stream)); CU(grow_keep(ctx->d_lr, total, l0, ctx->stream));
+    asb::TextTabs T;
+    T.idx_sorted = ctx->d_t_idx.p; T.pos_len = ctx->d_pos_len.p; T.lbase = ctx->d_t_lbase.p; T.soff = ctx->d_t_soff.p; T.milli = ctx->d_t_milli.p;
+    T.sbuf = reinterpret_cast<const char*>(ctx->d_t_sbuf.p); T.n_pos = ctx->t_n_pos; T.lbase_len = ctx->t_lbase_len; T.n_strings = ctx->t_n_strings;
+    CU(cudaMemsetAsync(ctx->d_ctr.p + asb::C_ERR, 0, sizeof(unsigned long long), ctx->stream));
+    asb::asb_lines_from_records_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(dev_recs, n, T, ctx->d_la.p + l0, ctx->d_lb.p + l0, ctx->d_lm.p + l0,
+                                                                                        ctx->d_lr.p + l0, ctx->d_ctr.p + asb::C_ERR);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    CU(cudaMemcpyAsync(&ctx->h_ctr[0], ctx->d_ctr.p + asb::C_ERR, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_ctr[0]) return fail(ctx, ASB_E_ARG, "a record has no entry in the iden string table (asb_text_begin)");
     ctx->n_lines += n;
     return ASB_OK;
 }

@@ -113,18 +113,20 @@ def agree(ok: bool, dev, what: str = ""):
         raise DistributedAbort(f"amplicon_sorter_b200: rank {dist.get_rank()}: a rank failed in {what or 'a sharded call'}; aborting all ranks")
 
 
-def gather_step(mine, status: int, done: bool, dev):
-    """Per-slab K6: the ranks' record tensors ((k, 4) int32 on `dev`, each sorted) -> their concatenation on rank 0
-    (None elsewhere), all on the device: counts all_gather, padded gather over NCCL / NVLink, no host round trip.
-    The counts message also carries every rank's status and done flag, so that a failed rank (or ranks that disagree
-    on the number of slabs) stops ALL ranks at the same step instead of leaving them parked in a collective."""
+def gather_step(mine, status: int, done: bool, dev, extra: int = 0):
+    """Per-slab K6: the ranks' record tensors ((k, 4) int32 on `dev`, each sorted) -> their concatenation in rank order
+    on rank 0 (None elsewhere), all on the device: counts all_gather, padded gather over NCCL / NVLink, no host round
+    trip.  The counts message also carries every rank's status and done flag, so that a failed rank (or ranks that
+    disagree on the number of slabs) stops ALL ranks at the same step instead of leaving them parked in a collective --
+    and one more integer per rank (`extra`: the bytes its piece of the slab prints to).
+    Returns (records on rank 0 | None, done, list of every rank's extra)."""
     import torch
     import torch.distributed as dist
 
     w, r = dist.get_world_size(), dist.get_rank()
     n = int(mine.shape[0]) if mine is not None else 0
-    head = torch.tensor([n, int(status), int(bool(done))], dtype=torch.int64, device=dev)
-    heads = torch.empty((w, 3), dtype=torch.int64, device=dev)
+    head = torch.tensor([n, int(status), int(bool(done)), int(extra)], dtype=torch.int64, device=dev)
+    heads = torch.empty((w, 4), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(heads, head) if dev.type == "cuda" else dist.all_gather(list(heads.unbind(0)), head)
     heads = heads.tolist()
     if any(h[1] for h in heads):
@@ -133,19 +135,20 @@ def gather_step(mine, status: int, done: bool, dev):
     dones = {h[2] for h in heads}
     if len(dones) != 1:
         raise DistributedAbort(f"amplicon_sorter_b200: rank {r}: ranks disagree on the number of slabs; aborting all ranks")
+    extras = [h[3] for h in heads]
     if dones.pop():
-        return None, True
+        return None, True, extras
     sizes = [h[0] for h in heads]
     mx = max(sizes)
     if mx == 0:
-        return (mine[:0] if r == 0 else None), False
+        return (mine[:0] if r == 0 else None), False, extras
     pad = torch.empty((mx, 4), dtype=torch.int32, device=dev)
     pad[:n] = mine
     buf = torch.empty((w, mx, 4), dtype=torch.int32, device=dev) if r == 0 else None
     dist.gather(pad, list(buf.unbind(0)) if r == 0 else None, dst=0)
     if r != 0:
-        return None, False
-    return torch.cat([buf[i, :s] for i, s in enumerate(sizes)]), False
+        return None, False, extras
+    return torch.cat([buf[i, :s] for i, s in enumerate(sizes)]), False, extras
 
 
 def gather_records(recs: np.ndarray, dev, status: int = 0):
@@ -153,7 +156,7 @@ def gather_records(recs: np.ndarray, dev, status: int = 0):
     import torch
 
     mine = torch.from_numpy(np.ascontiguousarray(recs).view(np.uint32).reshape(-1, 4).view(np.int32).copy()).to(dev)
-    allr, _ = gather_step(mine, status, False, dev)
+    allr, _, _ = gather_step(mine, status, False, dev)
     if allr is None:
         return None
     key = (allr[:, 0].to(torch.int64) << 32) | (allr[:, 1].to(torch.int64) & 0xFFFFFFFF)
@@ -210,10 +213,14 @@ class ShardedEngine(EngineBase):
         merged, printed there (csrc/text.cuh) and handed to `sink`; the resident line set ends up on rank 0's engine."""
         import torch.distributed as dist
 
+        idx_sorted, lbase, soff, milli, sbuf = text_tables
         job = broadcast_job({"op": "batch_text", "order": np.asarray(order, np.uint32), "hi": np.asarray(hi, np.uint32),
-                             "dpass": np.asarray(dpass, np.uint32), "drev": np.asarray(drev, np.uint32)}, self.dev)
+                             "dpass": np.asarray(dpass, np.uint32), "drev": np.asarray(drev, np.uint32),
+                             "t_idx": np.asarray(idx_sorted, np.uint32), "t_lbase": np.asarray(lbase, np.uint32), "t_soff": np.asarray(soff, np.uint32),
+                             "t_milli": np.asarray(milli, np.uint16), "t_sbuf": np.frombuffer(sbuf, dtype=np.uint8),
+                             "path": getattr(sink, "path", None), "base": int(getattr(sink, "pos", 0))}, self.dev)
         try:
-            return _run_shard_text(self.engine, job, self.dev, dist.get_rank(), dist.get_world_size(), text_tables, sink)
+            return _run_shard_text(self.engine, job, self.dev, dist.get_rank(), dist.get_world_size(), sink)
         except DistributedAbort:
             self.aborted = True
             raise
@@ -273,64 +280,82 @@ def _sum_totals(tot, dev):
     return {k: (int(v) if isinstance(tot[k], int) else float(v)) for k, v in zip(keys, t.tolist())}
 
 
-def _run_shard_text(engine, job, dev, r, w, text_tables, sink):
-    """One rank's part of ShardedEngine.compare_text (rank 0 prints, ranks > 0 only compare and send)."""
+def _run_shard_text(engine, job, dev, r, w, sink):
+    """One rank's part of ShardedEngine.compare_text.  Every rank compares its contiguous piece of every slab, prints
+    ITS OWN lines (second CUDA stream + helper thread, while the next slab is compared) and writes them at its own
+    offset of the tempfile: one small all_gather per slab (record counts, status, done flag, bytes of the piece) fixes
+    the offsets, so formatting, the device-to-host copy and write(2) all scale with the ranks.  The records are also
+    gathered on rank 0's GPU (NCCL), where they become the resident integer lines of the later stages."""
+    from . import host
     from .engine import TOTALS
 
     tot = dict.fromkeys(TOTALS, 0)
     tot["steps"] = 0
     status = 0
+    my_sink = sink
     try:
         engine.batch_begin(job["order"], job["hi"], job["dpass"], job["drev"], r, w)
-        if r == 0:
-            engine.text_begin(*text_tables)
+        engine.text_begin(job["t_idx"], job["t_lbase"], job["t_soff"], job["t_milli"], job["t_sbuf"].tobytes())
+        if r != 0:
+            my_sink = host.TextSink(job["path"], existing=True) if job["path"] else host.NullSink()
     except Exception:  # noqa: BLE001
         import traceback
 
         traceback.print_exc()
         status = 1
-    n_rec = 0
-    submit, pending = (engine._text_async(sink), None) if r == 0 else (None, None)
+    n_rec, file_pos = 0, int(job["base"])
+    submit, pending = engine._text_async(my_sink, append_lines=False), None
     try:
         while True:
-            info, mine = None, None
+            info, mine, nbytes = None, None, 0
             if not status:
                 try:
                     info = engine.batch_step()
+                    if pending is not None:  # the previous slab's text went out while this slab was compared
+                        pending.result()
+                        pending = None
                     if info is not None:
                         mine = engine.step_records_tensor(info["n_records"], dev)
-                except Exception:  # noqa: BLE001
+                        if info["n_records"]:
+                            engine.text_load(None, info["n_records"])
+                            nbytes = engine.text_measure()
+                except Exception:  # noqa: BLE001 -- gather_step tells every rank
                     import traceback
 
                     traceback.print_exc()
                     status = 1
-            if pending is not None:  # rank 0: the previous slab's text went out while this slab was compared
-                try:
-                    pending.result()
-                except Exception:  # noqa: BLE001 -- gather_step tells the other ranks
-                    import traceback
-
-                    traceback.print_exc()
-                    status = 1
-                pending = None
-            merged, done = gather_step(mine, status, info is None, dev)  # raises DistributedAbort on every rank if any failed
+            merged, done, sizes = gather_step(mine, status, info is None, dev, nbytes)  # raises DistributedAbort on every rank if any failed
             if done:
                 break
             for k in TOTALS:
                 tot[k] += info.get(k, 0)
             tot["steps"] += 1
-            if r == 0 and merged is not None and merged.shape[0]:
-                n_rec += int(merged.shape[0])
-                try:
-                    pending = submit(engine.text_load_tensor(merged, sort=w > 1))
-                except Exception:  # noqa: BLE001 -- the next gather_step tells the other ranks
-                    import traceback
+            try:
+                if nbytes:
+                    my_sink.seek(file_pos + sum(sizes[:r]))
+                    pending = submit(info["n_records"])
+                file_pos += sum(sizes)
+                if r == 0 and merged is not None and merged.shape[0]:
+                    n_rec += int(merged.shape[0])
+                    engine.lines_append_tensor(merged)
+            except Exception:  # noqa: BLE001 -- the next gather_step tells the other ranks
+                import traceback
 
-                    traceback.print_exc()
-                    status = 1
+                traceback.print_exc()
+                status = 1
     finally:
-        if pending is not None:
-            pending.result()
+        err = None
+        try:
+            if pending is not None:
+                pending.result()
+            if r != 0:
+                my_sink.close()
+        except Exception as exc:  # noqa: BLE001
+            import traceback
+
+            traceback.print_exc()
+            err = exc
+    agree(err is None, dev, "writing the tempfile")  # also the barrier: rank 0 returns when every piece is in the file
     tot = _sum_totals(tot, dev)
     tot["n_records"] = n_rec
     return tot
@@ -416,4 +441,4 @@ def worker_loop(engine, dev):
         elif op == "region_end":
             _region_end(dev)
         elif op == "batch_text":
-            _run_shard_text(engine, job, dev, dist.get_rank(), dist.get_world_size(), None, None)
+            _run_shard_text(engine, job, dev, dist.get_rank(), dist.get_world_size(), None)

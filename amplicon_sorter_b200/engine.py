@@ -41,7 +41,7 @@ class EngineBase:
 
     _pool = None
 
-    def _text_async(self, sink):
+    def _text_async(self, sink, append_lines: bool = True):
         """Lines of the staged record set -> sink, on a helper thread (the text stage has its own CUDA stream): the
         comparison of the next slab runs meanwhile.  Returns a future; wait for it before the next text_load."""
         if self._pool is None:
@@ -50,7 +50,7 @@ class EngineBase:
             self._pool = ThreadPoolExecutor(1, thread_name_prefix="asb200-text")
 
         def emit(n):
-            for chunk in self.text_chunks(n):
+            for chunk in self.text_chunks(n, append_lines):
                 sink(chunk)
 
         return lambda n: self._pool.submit(emit, n)
@@ -282,18 +282,30 @@ class Engine(EngineBase):
             sl.ptr, sl.cap = p.value, want
         return sl
 
-    def text_step(self, first: int, count: int) -> TextChunk:
-        """Lines of records [first, first + count) of the current record set (the last step's, or text_load's)."""
+    def text_step(self, first: int, count: int, append_lines: bool = True) -> TextChunk:
+        """Lines of records [first, first + count) of the staged record set (text_load).  append_lines: also append
+        them in integer form to the resident line set (off when they get there through lines_append_tensor)."""
         sl = self._acquire_slot(_ffi.TEXT_MAX_LINE * int(count) + 64)
         nb = C.c_uint64()
-        self._check(self._lib.asb_text_step(self._h, int(first), int(count), C.c_void_p(sl.ptr), sl.cap, C.byref(nb)))
+        self._check(self._lib.asb_text_step(self._h, int(first), int(count), int(bool(append_lines)), C.c_void_p(sl.ptr), sl.cap, C.byref(nb)))
         sl.free.clear()
         return TextChunk(memoryview((C.c_char * nb.value).from_address(sl.ptr)).cast("B"), sl)
 
-    def text_chunks(self, n_records: int):
-        """The current record set as text, in chunks of at most TEXT_CHUNK records, in file order."""
+    def text_chunks(self, n_records: int, append_lines: bool = True):
+        """The staged record set as text, in chunks of at most TEXT_CHUNK records, in file order."""
         for first in range(0, int(n_records), _ffi.TEXT_CHUNK):
-            yield self.text_step(first, min(_ffi.TEXT_CHUNK, int(n_records) - first))
+            yield self.text_step(first, min(_ffi.TEXT_CHUNK, int(n_records) - first), append_lines)
+
+    def text_measure(self) -> int:
+        """Bytes the staged record set prints to."""
+        nb = C.c_uint64()
+        self._check(self._lib.asb_text_measure(self._h, C.byref(nb)))
+        return int(nb.value)
+
+    def lines_append_tensor(self, recs):
+        """Append an (n, 4) int32 tensor of records on this GPU, already in file order, to the resident line set."""
+        if int(recs.shape[0]):
+            self._check(self._lib.asb_lines_append_dev(self._h, C.c_void_p(recs.data_ptr()), int(recs.shape[0])))
 
     def text_load(self, dev_ptr: int | None, n_records: int, sort: bool = True):
         """Stage the record set of the text stage: the last step's records (dev_ptr None), or n_records asb_records in

@@ -144,14 +144,19 @@ class TextSink:
 
     THREADS = 4
 
-    def __init__(self, path: str):
+    def __init__(self, path: str, existing: bool = False):
         import queue
         import threading
 
-        self.fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_APPEND, 0o666)  # :803 append mode ...
-        self.base = os.lseek(self.fd, 0, os.SEEK_END)
-        os.close(self.fd)
+        self.path = path
+        if existing:  # a worker rank writing its pieces into the file rank 0 created
+            self.base = 0
+        else:
+            self.fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_APPEND, 0o666)  # :803 append mode ...
+            self.base = os.lseek(self.fd, 0, os.SEEK_END)
+            os.close(self.fd)
         self.fd = os.open(path, os.O_WRONLY)  # ... realised with explicit offsets (pwrite ignores them under O_APPEND)
+        self.pos = self.base  # where the next chunk goes
         self.q = queue.Queue()
         self.err = None
         self.bytes = 0
@@ -159,9 +164,14 @@ class TextSink:
         for t in self.threads:
             t.start()
 
+    def seek(self, offset: int):
+        """The next chunks go to `offset` onwards (multi-GPU: this rank's piece of a slab)."""
+        self.pos = int(offset)
+
     def __call__(self, chunk):
         n = len(chunk.data)
-        self.q.put((chunk, self.base + self.bytes))
+        self.q.put((chunk, self.pos))
+        self.pos += n
         self.bytes += n
 
     def _run(self):
@@ -189,6 +199,26 @@ class TextSink:
         os.close(self.fd)
         if self.err is not None:
             raise self.err
+
+
+class NullSink:
+    """Drops the text (measurement runs: the lines are assembled and copied out, not written)."""
+
+    path = None
+    base = 0
+
+    def __init__(self):
+        self.bytes = 0
+
+    def seek(self, offset: int):
+        pass
+
+    def __call__(self, chunk):
+        self.bytes += len(chunk.data)
+        chunk.release()
+
+    def close(self):
+        pass
 
 
 class AllPairs:

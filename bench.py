@@ -233,17 +233,6 @@ def _reference_script_record():
         return None
 
 
-class NullSink:
-    """Resident arm: the text of every slab is produced (device formatting + D2H into pinned memory) and dropped."""
-
-    def __init__(self):
-        self.bytes = 0
-
-    def __call__(self, chunk):
-        self.bytes += len(chunk.data)
-        chunk.release()
-
-
 def parity_check(facade, world):
     """Before anything is timed: a small job of the same kind through host.process_list on THIS engine stack (all
     ranks, NCCL gather, device-side text) must give the file the CPU oracle writes."""
@@ -329,7 +318,7 @@ def main():
     codes_bytes = 2 * int(w["buf"].nbytes)  # forward + compl_reverse symbol codes
     flush_buf = None if codes_bytes > 126 * (1 << 20) else torch.empty(192 * (1 << 20), dtype=torch.uint8, device=dev)
     facade.upload_reads(w["buf"], w["offs"])
-    sink = NullSink()
+    sink = host.NullSink()
 
     def job():
         return facade.compare_text(w["order"], w["hi"], w["dpass"], w["drev"], w["tables"], sink)

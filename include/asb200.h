@@ -95,7 +95,9 @@ int asb_upload_reads_dev(asb_ctx *ctx, const uint8_t *dev_ascii, const uint64_t 
  * order[n] = read ids in the stable length-sorted order of :669; hi[p] = last position j kept by the window test :679 for row p
  * (hi[p] >= p; hi[p] == p means no partner); dpass/drev[L] = integer cut-offs for a longer read
  * of length L (see thresholds.py): pass iff d <= dpass[L]; retry on compl_reverse iff d >= drev[L].
- * (rank, world) shards the rows cyclically (row p of the sorted batch belongs to rank p % world); a single GPU is (0, 1). */
+ * (rank, world) shards the work: the rows of every step (slab) are split into `world` contiguous ranges of equal pair
+ * counts and rank k takes the k-th, so the records of rank k are the k-th contiguous piece of the step's lines; every
+ * rank steps through the same slabs.  A single GPU is (0, 1). */
 int asb_batch_begin(asb_ctx *ctx, const uint32_t *order, uint32_t n, const uint32_t *hi,
                     const uint32_t *dpass, const uint32_t *drev, uint32_t table_len,
                     uint32_t rank, uint32_t world);
@@ -119,8 +121,9 @@ int64_t asb_format_records(const asb_record *recs, uint64_t n, const uint32_t *i
  * string number lbase[L] + d at sbuf[soff[e] .. soff[e+1]) (lbase[L] = 0xFFFFFFFF: no string for that length) with
  * milli[e] = iden * 1000.  It also empties the context's resident line set (asb_lines_*): a new tempfile starts.
  * asb_text_step turns records [first, first + count) of the CURRENT record set into lines "idxA:idxB:iden[:reverse]\n"
- * in (i_pos, j_pos) order, copies the text to host_dst (cap bytes; pinned memory from asb_host_alloc) and APPENDS the
- * same lines in integer form to the resident line set, so SSG / the best-hit filters run without parsing the file.
+ * in (i_pos, j_pos) order, copies the text to host_dst (cap bytes; pinned memory from asb_host_alloc) and, with
+ * append_lines != 0, APPENDS the same lines in integer form to the resident line set, so SSG / the best-hit filters run
+ * without parsing the file.
  * Call it with consecutive ranges (writer threads append one chunk while the next is assembled).  The current
  * record set is what asb_text_load staged: dev_recs == NULL -> the sorted output of the last asb_batch_step; else n
  * records in DEVICE memory, e.g. the NCCL gather of several ranks' lists (sort != 0 orders them by (i_pos, j_pos)).
@@ -130,7 +133,14 @@ int64_t asb_format_records(const asb_record *recs, uint64_t n, const uint32_t *i
 int asb_text_begin(asb_ctx *ctx, const uint32_t *idx_sorted, uint32_t n_pos, const uint32_t *lbase, uint32_t lbase_len,
                    const uint32_t *soff, const uint16_t *milli, uint32_t n_strings, const char *sbuf, uint32_t sbuf_len);
 int asb_text_load(asb_ctx *ctx, const asb_record *dev_recs, uint64_t n, int sort);
-int asb_text_step(asb_ctx *ctx, uint64_t first, uint64_t count, char *host_dst, uint64_t cap, uint64_t *nbytes);
+int asb_text_step(asb_ctx *ctx, uint64_t first, uint64_t count, int append_lines, char *host_dst, uint64_t cap,
+                  uint64_t *nbytes);
+/* Multi-GPU: every rank prints ITS OWN contiguous piece of a step's lines.  asb_text_measure = bytes the staged record
+ * set will print to (so the ranks can agree on file offsets before anything is written); asb_text_step with
+ * append_lines = 0 prints without touching the resident line set; asb_lines_append_dev appends n records in device
+ * memory (the NCCL gather of the ranks' pieces, already in file order) to the resident line set without printing. */
+int asb_text_measure(asb_ctx *ctx, uint64_t *nbytes);
+int asb_lines_append_dev(asb_ctx *ctx, const asb_record *dev_recs, uint64_t n);
 /* Pinned host memory for the text (no context needed). */
 int asb_host_alloc(uint64_t bytes, void **out);
 void asb_host_free(void *p);

@@ -51,10 +51,18 @@ class OracleEngine(EngineBase):
         self._staged = r
         return int(r.shape[0])
 
-    def text_chunks(self, n_records):
-        return [self._format(self._staged)] if n_records else []
+    def text_chunks(self, n_records, append_lines=True):
+        return [self._format(self._staged, append_lines)] if n_records else []
 
-    def _format(self, recs):
+    def text_measure(self):
+        return len(self._format(self._staged, False).data)
+
+    def lines_append_tensor(self, recs):
+        r = recs.cpu().numpy().view(np.uint32).reshape(-1).view(RECORD)
+        if r.shape[0]:
+            self._format(r, True)
+
+    def _format(self, recs, append_lines=True):
         idx, lbase, soff, milli, sbuf = self._tabs
         out, a, b, m, rv = [], [], [], [], []
         for i, j, d, rev in recs.tolist():
@@ -62,8 +70,9 @@ class OracleEngine(EngineBase):
             assert lbase[self._lens_sorted[j]] != 0xFFFFFFFF and e < milli.shape[0]
             out.append(b"%d:%d:%s%s\n" % (idx[i], idx[j], sbuf[soff[e]:soff[e + 1]], b":reverse" if rev else b""))
             a.append(idx[i]); b.append(idx[j]); m.append(milli[e]); rv.append(bool(rev))
-        self._res = [np.concatenate([x, np.asarray(y, dtype=x.dtype)]) for x, y in zip(self._res, (a, b, m, rv))]
-        self._lines = tuple(self._res[:3])  # the printed lines are the resident line set
+        if append_lines:
+            self._res = [np.concatenate([x, np.asarray(y, dtype=x.dtype)]) for x, y in zip(self._res, (a, b, m, rv))]
+            self._lines = tuple(self._res[:3])  # the printed lines are the resident line set
         return TextChunk(b"".join(out))
 
     def lines_count(self):
@@ -92,7 +101,7 @@ class OracleEngine(EngineBase):
             cnt = int(hi[i]) - i
             if cnt <= 0:
                 continue
-            if i % world != rank:  # rows are dealt cyclically, like the engine does
+            if (i * world) // max(n, 1) != rank:  # contiguous pieces in rank order, like the engine's (any such split will do)
                 continue
             js = np.arange(i + 1, int(hi[i]) + 1)
             pairs += js.size
