@@ -76,23 +76,26 @@ def _bcast_array(arr, dev, src=0, keep_on_device=False):
     return t.cpu().numpy().view(np.dtype(dt)).reshape(shape)
 
 
+INLINE_BYTES = 1 << 20  # arrays up to this size travel inside the job's pickle; larger ones as device tensors
+
+
 def broadcast_job(job: dict | None, dev):
-    """Rank 0 passes {'op': ..., arrays...}; every rank returns the same dict."""
+    """Rank 0 passes {'op': ..., arrays...}; every rank returns the same dict.  ONE object broadcast carries the op,
+    the scalars and every small array (a batch is a handful of 400 KB arrays: two dozen separate collectives cost
+    more than the comparison of a slab at 8 GPUs); only big arrays (the read bytes) go as tensors of their own."""
     import torch.distributed as dist
 
-    keys = [None]
+    box = [None]
     if dist.get_rank() == 0:
-        keys = [[(k, isinstance(v, np.ndarray)) for k, v in job.items()]]
-    dist.broadcast_object_list(keys, src=0)
+        box = [{k: (("__tensor__",) if isinstance(v, np.ndarray) and v.nbytes > INLINE_BYTES else v) for k, v in job.items()}]
+    dist.broadcast_object_list(box, src=0)
     out = {}
-    for k, is_arr in keys[0]:
-        if is_arr:
+    for k, v in box[0].items():
+        if isinstance(v, tuple) and v == ("__tensor__",):
             # the read bytes go straight from the broadcast buffer into the engine (no host round trip on any rank)
             out[k] = _bcast_array(job[k] if job is not None else None, dev, keep_on_device=(k == "buf" and dev.type == "cuda"))
         else:
-            box = [job[k] if job is not None else None]
-            dist.broadcast_object_list(box, src=0)
-            out[k] = box[0]
+            out[k] = v
     return out
 
 
