@@ -56,7 +56,8 @@ KNOWN_TEXT_CRC = {
     3: 3356075816,  # 916,299 lines, 17,988,322 bytes
     4: 3352788876,  # 62,448,413 lines, 1,339,098,740 bytes
     5: 1976580653,  # 24,887,125 lines, 539,029,280 bytes (same line count as every r1 kernel version)
-}  # all recorded before the pivot bound (asb_prune) existed: every pair went through the banded passes
+    6: 2667264339,  # 24,895,379 lines (recorded with --prune 0)
+}  # all recorded with every pair going through the banded passes (1-5: before the pivot bound existed; 6: --prune 0)
 DESCR = {
     1: "cfg1: default batch mode on 1,000 synthetic ~700 bp reads (5 templates)",
     2: "cfg2: --all on 10,000 synthetic reads, 3 genes (1.8 / 0.7 / 1.0 kb) x 4 species",
