@@ -79,8 +79,14 @@ struct DevBatch {
     const uint32_t* pos_read;  // [n] read id at sorted position p (nullptr: positions are read ids)
     int seed_on;               // 0 = off
     int seed_J;                // chunk entries per lane in shared memory
-    // shared memory per warp: [peq_words match masks][kSeedBitsPad query bitset][seed_J * 16 words of profiles]
-    int peq_words, warp_words;
+    // shared memory per warp: nslots x [peq_words match masks][kSeedBitsPad query bitset] (one slot per query of a
+    // group, slot_words apart), then [seed_J * 16 words of per-lane seed profiles]
+    int peq_words, warp_words, nslots, slot_words;
+    // list keys: row << 32 | norc << 31 | class << jbits | column.  The class (a few bits of the TARGET's cluster word:
+    // pivot, orientation, distance bucket) only ORDERS the entries of a row, so that the 32 lanes of a list warp hold
+    // targets that behave alike against the row's query (all pass, all die early, all die late); it never decides
+    // anything.  jbits == 0: no class bits (column = low 31 bits).
+    int jbits; uint32_t cls_pmask, cls_adiv;
 };
 
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
@@ -137,25 +143,41 @@ __device__ __forceinline__ void build_peq(uint32_t* peq, const DevBatch& B, cons
 
 struct LaneJob {
     bool valid;      // lane holds a pair
+    int slot;        // which of the group's (at most two) queries this lane's pair belongs to
     uint32_t j;      // target position
+    uint32_t low;    // low key word without the norc bit (class bits | column): what the pair carries into the next list
     uint32_t zval;   // M_ZONE: d_rc carried by the entry
     uint64_t entry;  // M_EXACT: output slot
     int strand;      // M_EXACT
     bool norc;       // M_FWD: the compl_reverse strand of this pair is already proven > dpass (cluster pruning)
 };
 
-// All lanes with valid==true share query `row`.  Runs the mode's passes and routes the results.
+// Lanes with valid==true hold pairs of query `row0` (slot 0) or `row1` (slot 1).  row1 == row0: the group has one
+// query.  A second query rides along only in the list passes M_FWD / M_RC / M_ZONE (asb_lists pairs the tail of one
+// row-run with the head of the next, so that a 32-entry slice is ONE group instead of two half-empty ones) and only
+// when both queries are non-empty.  Everything that depends on the query (length, match masks, q-mer bitset) is per
+// lane; the lanes only share the code path.  Runs the mode's passes and routes the results.
 template <int BT>
-__device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, const int mode, const uint32_t row,
+__device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* wsm, const int mode, const uint32_t row0, const uint32_t row1,
                                               const LaneJob job, unsigned long long& cols_acc, unsigned& useful_acc)
 {
-    const int m = (int)B.pos_len[row];
-    const uint8_t* q = B.codes_f + B.pos_off[row];
-    const int W = (m + 31) >> 5;
+    const bool two = row1 != row0;
+    const int m0 = (int)B.pos_len[row0];
+    const int m1 = two ? (int)B.pos_len[row1] : m0;
+    const uint8_t* q0 = B.codes_f + B.pos_off[row0];
+    const uint8_t* q1 = two ? B.codes_f + B.pos_off[row1] : q0;
+    const bool s1 = two && job.slot != 0;
+    const uint32_t row = s1 ? row1 : row0;      // per lane from here on
+    const int m = s1 ? m1 : m0;
+    const int W0 = (m0 + 31) >> 5, W1 = (m1 + 31) >> 5;
+    const int W = W0 > W1 ? W0 : W1;            // warp-uniform
+    uint32_t* peq0 = wsm;
+    uint32_t* peq1 = wsm + B.slot_words;
+    const uint32_t* peq = s1 ? peq1 : peq0;
     int n = m, k = -1;
     bool ok = job.valid;
-    const uint8_t* tf = q;
-    const uint8_t* tr = q;
+    const uint8_t* tf = q0;
+    const uint8_t* tr = q0;
     if (job.valid) {
         n = (int)B.pos_len[job.j];
         const uint64_t off = B.pos_off[job.j];
@@ -168,8 +190,9 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         else { const uint32_t kk = B.dpass[L]; k = kk == 0xFFFFFFFFu ? -1 : (int)kk; }
         if (abs(n - m) > k) ok = false;  // d >= |n-m| > k on either strand
     }
-    const uint64_t key = ((uint64_t)row << 32) | job.j;
-    if (m == 0) {  // empty query: d = n, no DP needed (never happens behind -min 300)
+    const uint64_t key = ((uint64_t)row << 32) | job.j;     // what a record carries
+    const uint64_t lkey = ((uint64_t)row << 32) | job.low;  // what the next list carries (class bits stay)
+    if (m0 == 0) {  // empty query: d = n, no DP needed (never happens behind -min 300); such a group has one query
         const bool pass = ok && n <= k;
         if (mode == M_SCREEN || mode == M_FWD) warp_push(pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, ((uint32_t)n << 1), &B.ctr[C_ERR]);
         if (mode == M_ZONE) warp_push(job.valid && !pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, (job.zval << 1) | 1u, &B.ctr[C_ERR]);
@@ -199,10 +222,10 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         return;
     }
     const int full_cols = (nmax + 31) & ~31;
-    if (BT == 0 && mode == M_EXACT && B.ex_hw) {  // infix distance: full matrix, free top row
-        build_peq(peq, B, q, m, W);
+    if (BT == 0 && mode == M_EXACT && B.ex_hw) {  // infix distance: full matrix, free top row (one query per group)
+        build_peq(peq0, B, q0, m0, W0);
         const uint8_t* t = job.strand ? tr : tf;
-        const int best = hw_pass(peq, B.Wpad, W, m, t, n, nmax, cols_acc);
+        const int best = hw_pass(peq0, B.Wpad, W0, m0, t, n, nmax, cols_acc);
         if (job.valid) B.ex_out[job.entry] = best;
         return;
     }
@@ -215,21 +238,26 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         g.cont = B.cont_thresh;
         push = B.push_thresh;
     }
-    build_peq(peq, B, q, m, W);
-    // seed lower bound: the query's q-mer presence bitset goes next to its match masks
+    build_peq(peq0, B, q0, m0, W0);
+    if (two) build_peq(peq1, B, q1, m1, W1);
+    // seed lower bound: every query's q-mer presence bitset goes next to its match masks
     SeedLB sl;
     sl.hs = nullptr; sl.J = 0;
     const bool use_seeds = B.seed_on && mode != M_ZONE && !(mode == M_EXACT && B.ex_cap < 0);
-    uint32_t* qb = peq + B.peq_words;
-    uint16_t* hs_lane = reinterpret_cast<uint16_t*>(qb + kSeedBitsPad) + (threadIdx.x & 31);
+    const uint32_t* qb = (s1 ? peq1 : peq0) + B.peq_words;  // this lane's query
+    uint16_t* hs_lane = reinterpret_cast<uint16_t*>(wsm + B.nslots * B.slot_words) + (threadIdx.x & 31);
     const uint4* sf = nullptr;
     const uint4* sr = nullptr;
     int nch = 0;
     if (use_seeds) {
-        const uint32_t rid = B.pos_read ? B.pos_read[row] : row;
-        const uint4* src = reinterpret_cast<const uint4*>(B.qbits + (size_t)rid * kSeedWords);
-        for (int x = threadIdx.x & 31; x < kSeedBitsPad / 4; x += 32)
-            reinterpret_cast<uint4*>(qb)[x] = x < kSeedWords / 4 ? __ldg(src + x) : make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (int s = 0; s < (two ? 2 : 1); ++s) {
+            const uint32_t r = s ? row1 : row0;
+            const uint32_t rid = B.pos_read ? B.pos_read[r] : r;
+            const uint4* src = reinterpret_cast<const uint4*>(B.qbits + (size_t)rid * kSeedWords);
+            uint4* dst = reinterpret_cast<uint4*>((s ? peq1 : peq0) + B.peq_words);
+            for (int x = threadIdx.x & 31; x < kSeedBitsPad / 4; x += 32)
+                dst[x] = x < kSeedWords / 4 ? __ldg(src + x) : make_uint4(~0u, ~0u, ~0u, ~0u);
+        }
         __syncwarp();
         if (job.valid) {
             const uint32_t tid = B.pos_read ? B.pos_read[job.j] : job.j;
@@ -247,7 +275,7 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
         const uint8_t* t = (phase == 1 || (mode == M_EXACT && job.strand)) ? tr : tf;
         int st, sc;
         if (use_seeds) sl.J = seed_profile(qb, (t == tr) ? sr : sf, ok ? nch : 0, hs_lane, B.seed_J);
-        band_pass<BT>(peq, B.Wpad, W, m, t, n, k, ok, g, push, sl, st, sc, cols_acc, useful_acc);
+        band_pass<BT>(peq, B.Wpad, m, t, n, k, ok, g, push, sl, st, sc, cols_acc, useful_acc);
         const bool pass = ok && st == PASS_DONE && sc <= k;
         const bool surv = ok && st == PASS_SURVIVOR;
         if (phase == 0) {
@@ -260,15 +288,15 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* peq, 
                 return;
             }
             warp_push(pass, B.O, B.Ov, &B.ctr[C_O], B.list_cap, key, ((uint32_t)sc << 1), &B.ctr[C_ERR]);  // AS:791-793
-            if (mode == M_SCREEN) warp_push(surv, B.F, nullptr, &B.ctr[C_F], B.list_cap, key, 0u, &B.ctr[C_ERR]);
+            if (mode == M_SCREEN) warp_push(surv, B.F, nullptr, &B.ctr[C_F], B.list_cap, lkey, 0u, &B.ctr[C_ERR]);
             const bool need_rc = ok && !pass && !surv;  // proven d_fwd > dpass
-            if (mode == M_FWD) { warp_push(need_rc && !job.norc, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]); return; }
+            if (mode == M_FWD) { warp_push(need_rc && !job.norc, B.R, nullptr, &B.ctr[C_R], B.list_cap, lkey, 0u, &B.ctr[C_ERR]); return; }
             ok = need_rc;
             if (__ballot_sync(0xFFFFFFFFu, ok) == 0u) return;
         } else {
             // compl_reverse strand (AS:795): same band, k = dpass
-            warp_push(pass, B.Z, B.Zv, &B.ctr[C_Z], B.list_cap, key, (uint32_t)sc, &B.ctr[C_ERR]);
-            if (mode == M_SCREEN) warp_push(surv, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_ERR]);
+            warp_push(pass, B.Z, B.Zv, &B.ctr[C_Z], B.list_cap, lkey, (uint32_t)sc, &B.ctr[C_ERR]);
+            if (mode == M_SCREEN) warp_push(surv, B.R, nullptr, &B.ctr[C_R], B.list_cap, lkey, 0u, &B.ctr[C_ERR]);
         }
     }
 }
@@ -303,9 +331,9 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? 4 : 1) asb_screen(c
         LaneJob job;
         job.j = row + 1 + gi * 32 + lane;
         job.valid = job.j <= B.hi[row];
-        job.zval = 0; job.entry = 0; job.strand = 0; job.norc = false;
+        job.zval = 0; job.entry = 0; job.strand = 0; job.norc = false; job.slot = 0; job.low = job.j;
         if (__ballot_sync(0xFFFFFFFFu, job.valid) == 0u) continue;  // a shorter row of the block: no such group
-        process_group<BT>(B, peq, M_SCREEN, row, job, cols_acc, useful_acc);
+        process_group<BT>(B, peq, M_SCREEN, row, row, job, cols_acc, useful_acc);
     }
     if (lane == 0 && cols_acc) atomicAdd(&B.ctr[C_WORDS], cols_acc);
     const unsigned long long useful_warp = warp_sum_u64(useful_acc);
@@ -313,8 +341,8 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? 4 : 1) asb_screen(c
 }
 
 // --------------------------------------------------------------------------------------------
-// asb_lists: persistent warps pull 32-entry slices of a (row, column)-sorted list; a slice that
-// spans several rows is processed one row-run at a time.
+// asb_lists: persistent warps pull 32-entry slices of a (row, class, column)-sorted list; a slice that
+// spans several rows is processed two row-runs at a time (one when the layout has a single query slot).
 // --------------------------------------------------------------------------------------------
 #ifndef ASB_LISTS_MINB9
 #define ASB_LISTS_MINB9 0
@@ -340,19 +368,32 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? ASB_LISTS_MINB9 : 0
         const bool have = e < B.list_n;
         const uint64_t key = have ? B.list[e] : 0;
         const uint32_t myrow = (uint32_t)(key >> 32);
+        const uint32_t jmask = B.jbits ? ((1u << B.jbits) - 1u) : 0x7FFFFFFFu;
         bool pending = have;
         for (;;) {
             const unsigned pm = __ballot_sync(0xFFFFFFFFu, pending);
             if (pm == 0u) break;
-            const uint32_t row = __shfl_sync(0xFFFFFFFFu, myrow, __ffs(pm) - 1);
+            const uint32_t row0 = __shfl_sync(0xFFFFFFFFu, myrow, __ffs(pm) - 1);
+            // the list is sorted by row: a slice holds the tail of one row-run and the head(s) of the next ones; the
+            // first two queries of the slice share a group when the layout has a second slot
+            uint32_t row1 = row0;
+            if (B.nslots > 1 && mode != M_EXACT) {
+                const unsigned pm2 = __ballot_sync(0xFFFFFFFFu, pending && myrow != row0);
+                if (pm2 != 0u) {
+                    const uint32_t r = __shfl_sync(0xFFFFFFFFu, myrow, __ffs(pm2) - 1);
+                    if (__ldg(&B.pos_len[row0]) != 0u && __ldg(&B.pos_len[r]) != 0u) row1 = r;
+                }
+            }
             LaneJob job;
-            job.valid = pending && myrow == row;
-            job.j = (uint32_t)key & 0x7FFFFFFFu;
+            job.valid = pending && (myrow == row0 || myrow == row1);
+            job.slot = (row1 != row0 && myrow == row1) ? 1 : 0;
+            job.j = (uint32_t)key & jmask;
+            job.low = (uint32_t)key & 0x7FFFFFFFu;
             job.norc = ((uint32_t)key >> 31) != 0u;  // set by asb_prune on F entries
             job.zval = (mode == M_ZONE && have) ? B.list_val[e] : 0u;
             job.entry = e;
             job.strand = (mode == M_EXACT && have) ? (int)B.ex_strand[e] : 0;
-            process_group<BT>(B, peq, mode, row, job, cols_acc, useful_acc);
+            process_group<BT>(B, peq, mode, row0, row1, job, cols_acc, useful_acc);
             pending = pending && !job.valid;
         }
     }
@@ -422,6 +463,7 @@ __global__ void __launch_bounds__(256) asb_prune(const DevBatch B)
             const uint32_t row = __ldg(&B.my_rows[r0 + local % nrw]);
             const uint32_t j = row + 1 + gi * 32 + lane;
             bool needF = false, needR = false, pr = false;
+            uint32_t cls = 0u;
             if (j <= __ldg(&B.hi[row])) {
                 const int m = (int)__ldg(&B.pos_len[row]), n = (int)__ldg(&B.pos_len[j]);  // n >= m: j follows row in the length order
                 const uint32_t kk = __ldg(&B.pos_k[j]);
@@ -438,10 +480,13 @@ __global__ void __launch_bounds__(256) asb_prune(const DevBatch B)
                     }
                     needF = !pf;
                     needR = pf && !pr;
+                    // class of the TARGET (sort order inside the row only): pivot | orientation | distance bucket
+                    if (B.jbits) cls = wb == kUncovered ? (B.cls_pmask << 4) | 15u
+                                                        : ((cw_pivot(wb) & B.cls_pmask) << 4) | (cw_orient(wb) << 3) | min(7u, cw_dist(wb) / B.cls_adiv);
                 }
             }
             // all 32 lanes take part in the warp-aggregated appends
-            const uint64_t key = ((uint64_t)row << 32) | j;
+            const uint64_t key = ((uint64_t)row << 32) | (cls << B.jbits) | j;
             warp_push(needF, B.F, nullptr, &B.ctr[C_F], B.list_cap, key | (pr ? 0x80000000ull : 0ull), 0u, &B.ctr[C_OVF]);
             warp_push(needR, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_OVF]);
         }
@@ -764,6 +809,11 @@ struct asb_ctx {
     // cluster pruning (ensure_clusters): per-read cluster words, pivot x pivot lower bounds, and what the batch decided
     DevBuf<uint32_t> d_cword, d_cl_u, d_cl_piv, d_cl_best, d_cl_pb, d_cl_vals; DevBuf<uint16_t> d_pivD; DevBuf<uint64_t> d_cl_keys; DevBuf<uint8_t> d_cl_st; DevBuf<int32_t> d_cl_out;
     int prune = 1;              // parameter "prune": 0 = never
+    int two_rows = 1;           // parameter "two_rows": list warps take the pairs of two queries at a time (process_group)
+    int class_sort = 1;         // parameter "class_sort": list entries of a row ordered by the target's cluster class (asb_prune)
+    int list_path = 1;          // parameter "list_path": clustered reads whose pairs the pivot bound cannot decide still take
+                                //   the class-sorted list passes instead of the screen kernel (0 = screen kernel, as before)
+    uint64_t slab_pairs = 1ull << 30;  // parameter "slab_pairs": pairs per slab over all ranks once pruning is known to work
     uint32_t prune_min_reads = 1024; uint64_t prune_min_pairs = 1ull << 22;  // below these a job is a few milliseconds anyway
     bool cl_ready = false; uint32_t cl_kmax = 0, cl_npiv = 0, cl_covered = 0;
     int prune_mode = 0;         // this batch: 0 = undecided, 1 = prune path, -1 = screen path
@@ -899,15 +949,29 @@ int peq_stride(int wmax, int bt) { return odd_stride(wmax + (bt > 0 ? bt : wmax)
 
 // Shared-memory layout of one warp (DevBatch::peq_words / warp_words) for Peq stride `Wpad`; `seeds` adds the
 // query's q-mer bitset and the per-lane seed profiles (only when the seed tables of the uploaded reads exist).
-void set_layout(const asb_ctx* ctx, DevBatch& B, int Wpad, bool seeds)
+void set_layout(const asb_ctx* ctx, DevBatch& B, int Wpad, bool seeds, int nslots = 1)
 {
     B.Wpad = Wpad;
     B.peq_words = (int)(((ctx->sigma + 1) * (uint32_t)Wpad + 3u) & ~3u);
     B.seed_on = seeds && ctx->seed_lb && ctx->seeds_ready;
     B.seed_J = std::min<int>(kSeedMaxChunks, std::max<int>(1, (int)((ctx->max_len / kSeedQ + 7) >> 3)));
-    B.warp_words = B.peq_words + (B.seed_on ? kSeedBitsPad + B.seed_J * 16 : 0);
+    int sw = B.peq_words + (B.seed_on ? kSeedBitsPad : 0);
+    if (nslots > 1) sw += (36 - (sw & 31)) & 31;  // slots 4 banks apart: equal rows of the two queries' tables do not collide
+    B.nslots = nslots; B.slot_words = sw;
+    B.warp_words = nslots * sw + (B.seed_on ? B.seed_J * 16 : 0);
     B.qbits = ctx->d_qbits.p; B.seed_off = ctx->d_seed_off.p;
     B.seeds_f = reinterpret_cast<const uint4*>(ctx->d_seeds_f.p); B.seeds_r = reinterpret_cast<const uint4*>(ctx->d_seeds_r.p);
+}
+
+// List passes: a second query slot per warp (process_group) unless the tables of one query are so large (long reads,
+// large alphabets) that doubling them would cost more occupancy than the fuller groups give back.
+int list_slots(const asb_ctx* ctx, DevBatch& B, int Wpad, bool seeds)
+{
+    if (!ctx->two_rows) { set_layout(ctx, B, Wpad, seeds, 1); return 1; }
+    set_layout(ctx, B, Wpad, seeds, 2);
+    if ((size_t)B.warp_words * sizeof(uint32_t) <= 12 * 1024) return 2;
+    set_layout(ctx, B, Wpad, seeds, 1);
+    return 1;
 }
 
 // 2-bit base of a symbol code (A,C,G,T = 0..3; anything else, and the padding code sigma, = 4)
@@ -1290,6 +1354,10 @@ int asb_set_param(asb_ctx* ctx, const char* name, double value)
     else if (!strcmp(name, "push_thresh")) { if (value < 0 || value > 31) return fail(ctx, ASB_E_ARG, "push_thresh in [0,31]"); ctx->push_thresh = (int)value; }
     else if (!strcmp(name, "seed_lb")) { ctx->seed_lb = value != 0; }
     else if (!strcmp(name, "prune")) { ctx->prune = value != 0; }
+    else if (!strcmp(name, "two_rows")) { ctx->two_rows = value != 0; }
+    else if (!strcmp(name, "class_sort")) { ctx->class_sort = value != 0; }
+    else if (!strcmp(name, "list_path")) { ctx->list_path = value != 0; }
+    else if (!strcmp(name, "slab_pairs")) { if (value < 1024) return fail(ctx, ASB_E_ARG, "slab_pairs too small"); ctx->slab_pairs = (uint64_t)value; }
     else if (!strcmp(name, "prune_min_reads")) { ctx->prune_min_reads = (uint32_t)std::max(0.0, value); ctx->cl_ready = false; }
     else if (!strcmp(name, "prune_min_pairs")) { ctx->prune_min_pairs = (uint64_t)std::max(0.0, value); }
     else if (!strcmp(name, "cont_thresh")) { if (value < 0 || value > 32) return fail(ctx, ASB_E_ARG, "cont_thresh in [0,32]"); ctx->cont_thresh = (int)value; }
@@ -1458,9 +1526,11 @@ static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, 
     uint64_t* keys; uint32_t* vals;
     // F: full forward pass
     float lists_ms = 0.f, ms = 0.f;
+    DevBatch BL = B;  // the list passes' own shared-memory layout (two query slots per warp)
+    list_slots(ctx, BL, B.Wpad, true);
     rc = sort_list(ctx, ctx->d_F.p, nullptr, nF, &keys, nullptr); if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
-    rc = run_list(ctx, B, M_FWD, cls, keys, nullptr, nF); if (rc) return rc;
+    rc = run_list(ctx, BL, M_FWD, cls, keys, nullptr, nF); if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[5], ctx->stream));
     rc = read_counters(ctx); if (rc) return rc;
     CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); lists_ms += ms;
@@ -1469,7 +1539,7 @@ static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, 
     // R: full compl_reverse pass
     rc = sort_list(ctx, ctx->d_R.p, nullptr, nR, &keys, nullptr); if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
-    rc = run_list(ctx, B, M_RC, cls, keys, nullptr, nR); if (rc) return rc;
+    rc = run_list(ctx, BL, M_RC, cls, keys, nullptr, nR); if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[5], ctx->stream));
     rc = read_counters(ctx); if (rc) return rc;
     CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); lists_ms += ms;
@@ -1480,7 +1550,7 @@ static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, 
     {
         const int zbt = kClasses[zcls];
         DevBatch BZ = B;
-        set_layout(ctx, BZ, peq_stride(wmax, zbt), false);
+        list_slots(ctx, BZ, peq_stride(wmax, zbt), false);
         CU(cudaEventRecord(ctx->ev[4], ctx->stream));
         rc = run_list(ctx, BZ, M_ZONE, zcls, keys, vals, nZ); if (rc) return rc;
         CU(cudaEventRecord(ctx->ev[5], ctx->stream));
@@ -1530,10 +1600,16 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
         }
     }
     const bool try_prune = ctx->prune_mode >= 0;
-    // slab: rows of one window class, at most pair_cap pairs (once pruning is known to work: 2^30, few pairs survive)
-    // (2^30 pairs per slab over ALL ranks: with more ranks the slabs must not become fewer, or nothing is left to overlap
-    // the gather and the text of a slab with)
-    const uint64_t slab_cap = ctx->prune_mode == 1 ? std::max<uint64_t>(ctx->pair_cap, (1ull << 30) / ctx->world) : ctx->pair_cap;
+    // slab: rows of one window class, at most pair_cap pairs per rank.  Once the list path is chosen, a slab is sized by
+    // what SURVIVES the pivot bound (at most 2^27 list entries per rank, 7 GB of lists) up to slab_pairs pairs over
+    // ALL ranks (default 2^30: with more ranks the slabs must not become fewer, or nothing is left to overlap the
+    // gather and the text of a slab with)
+    uint64_t slab_cap = ctx->pair_cap;
+    if (ctx->prune_mode == 1) {
+        const double keep = std::max(ctx->prune_left_ratio, 1.0 / 1024.0);
+        const uint64_t by_lists = (uint64_t)std::min<double>((double)(1ull << 27) / keep, 9.0e18);
+        slab_cap = std::max<uint64_t>(ctx->pair_cap, std::min<uint64_t>(ctx->slab_pairs / ctx->world, by_lists));
+    }
     const int cls = class_for(std::min(need_words(ctx, r0, ctx->h_pmax_dpass, 0), (int)((ctx->h_len[r0] + 31) / 32)));
     // Every slab's rows are split into `world` CONTIGUOUS ranges of (almost) equal pair counts, rank k takes the k-th:
     // a rank sees whole rows (long row-runs in its sorted lists), and its records are one contiguous piece of the
@@ -1617,6 +1693,10 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
             ctx->pos_tables_ready = true;
         }
         B.pos_cw = ctx->d_pos_cw.p; B.pos_k = ctx->d_pos_k.p;
+        if (ctx->class_sort) {  // class bits above the column bits of the list keys (asb_prune); needs >= 5 spare bits
+            const int jb = bits_for(n), cb = std::min(12, 31 - jb);
+            if (cb >= 5) { B.jbits = jb; B.cls_pmask = (1u << (cb - 4)) - 1u; B.cls_adiv = ctx->cl_kmax / 8 + 1; }
+        }
         // One pass appends the pairs the bound leaves for the exact passes.  The probe slab has screen-sized lists
         // (it may still fall back to the screen kernel); later slabs size their lists from the share that survived
         // so far and run again in the rare case that the estimate was too small.
@@ -1640,13 +1720,17 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
             lcap = left + 32;
         }
         ctx->prune_left_ratio = std::max(ctx->prune_left_ratio, (double)left / (double)std::max<uint64_t>(my_pairs, 1));
-        if (ctx->prune_mode == 0) ctx->prune_mode = 2 * left <= my_pairs ? 1 : -1;  // the probe slab decides for the batch
+        // the probe slab decides for the batch: the bound pays when it decides most pairs; when it does not, the reads
+        // still have cluster classes (ensure_clusters covered most of them), and the class-sorted list passes keep the
+        // lanes of a warp alike where the screen kernel's 32 consecutive targets are a mix of species and strands
+        if (ctx->prune_mode == 0) ctx->prune_mode = (2 * left <= my_pairs || (ctx->list_path && ctx->class_sort)) ? 1 : -1;
         if (ctx->prune_mode == 1) {
             pruned = true;
             info->pruned_pairs = my_pairs - left;
         }
     }
     if (!pruned) {
+        B.jbits = 0;  // the screen kernel's list entries carry no class
         rc = ensure_lists(ctx, std::max<uint64_t>(my_pairs, 32));
         if (rc) return rc;
         B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;

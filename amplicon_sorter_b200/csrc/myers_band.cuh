@@ -202,8 +202,8 @@ __device__ __forceinline__ void cols32_dispatch(const int len, uint32_t (&Pv)[NB
 }
 
 // Runs one banded pass for the 32 lanes of a warp (must be called by all 32 lanes).
-//   peq    : shared memory, row `sym` at peq + sym*Wpad, W real words then >= BT zero words
-//   m, W   : query length and ceil(m/32) (warp-uniform), m >= 1
+//   peq    : shared memory, THIS LANE's query: row `sym` at peq + sym*Wpad, ceil(m/32) real words then >= BT zero words
+//   m      : this lane's query length, m >= 1 (the lanes of a group share one query, or two: process_group)
 //   tgt    : this lane's target symbol codes (16-byte aligned, padded with the zero-row symbol)
 //   n, k   : this lane's target length (n >= m) and threshold; on = lane participates
 //   g      : warp-uniform band geometry (every participating lane's band fits in it)
@@ -242,7 +242,7 @@ __device__ __forceinline__ void cols32_dispatch(const int len, uint32_t (&Pv)[NB
 // Words dropped at the top never come back; a word (re-)entering at the bottom starts from Pv = all-ones
 // (vertical +1 edges below the word above).  With H = 0 this is the rule proven in DESIGN.md section 2.
 template <int BT>
-__device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, const int Wpad, const int W, const int m,
+__device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, const int Wpad, const int m,
                                        const uint8_t* __restrict__ tgt, const int n, const int k, const bool on,
                                        const BandGeom g, const int push_thresh, const SeedLB sl, int& status, int& score,
                                        unsigned long long& work, unsigned& useful)
@@ -252,7 +252,8 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
     constexpr int kGenUnroll = (BT > 0 && BT <= 9) ? ASB_GENERIC_UNROLL_NARROW : 1;  // columns of a target word unrolled in the general path
     const int Bmax = BT > 0 ? BT : g.Bw;
     uint32_t Pv[NB], Mv[NB];
-    const int wm = (m - 1) >> 5;  // word holding row m
+    const int wm = (m - 1) >> 5;  // word holding row m -- per lane: the lanes of a group may belong to two different queries
+    const int wmU = __reduce_max_sync(0xFFFFFFFFu, wm);  // words below a lane's own row m read zero match masks and are never used
     // this lane's own Ukkonen band: rows c - Dl .. c + El
     const int el = on ? (k - abs(n - m)) >> 1 : 0;
     const int Dl = el + max(n - m, 0), El = el + max(m - n, 0);
@@ -268,7 +269,7 @@ __device__ __forceinline__ void band_pass(const uint32_t* __restrict__ peq, cons
         if (seeds_right_of(0) > k) alive = false;  // more absent seeds than edits allowed: d > k without any DP
         if (__ballot_sync(0xFFFFFFFFu, alive) == 0u) { status = PASS_DEAD; score = 0; return; }
     }
-    int len = min(min(Bmax, g.T0 + 1), wm + 1);  // words computed per column -- warp-uniform (shared code path)
+    int len = min(min(Bmax, g.T0 + 1), wmU + 1);  // words computed per column -- warp-uniform (shared code path)
     if (alive) useful += (unsigned)min(min(len, ((31 + El) >> 5) + 1), wm + 1);  // words THIS lane needs in the first block
     if (BT > 0) len = min(BT, BT - ((BT - len) / STEP) * STEP);
 #pragma unroll

@@ -11,14 +11,16 @@ lines of <stem>_compare.tmp produced in the reference's order.
   python bench.py --impl reference ...                                   the CPU arm (oracle port, all host cores)
 
 Both arms go through the PRODUCT's code: a single GPU through `Engine`, N > 1 through `dist.ShardedEngine` on rank 0
-with the other ranks in `dist.worker_loop` (job broadcast, cyclic row shards, per-slab device-side NCCL gather).
+with the other ranks in `dist.worker_loop` (job broadcast, every slab's rows split into contiguous ranges of equal pair
+counts, every rank printing and writing its own piece of the tempfile, per-slab device-side NCCL gather of the records).
 
 value  : pairs/s with the reads already resident in HBM: `compare_text` (all slabs: screen + list kernels, sort, text
          assembled on the device and copied to pinned host memory) with the text dropped instead of written.
 e2e    : pairs/s of `host.process_list(comparelist2, tempfile)` -- the drop-in for amplicon_sorter.py:647 -- from
          Python lists of records to the finished <stem>_compare.tmp on disk: string join, H2D of the reads, all slabs,
          D2H of the text, write(2).  This is the call the reference script makes.
-roofline: the dominant kernel asb_screen is integer-ALU bound; see DESIGN.md section 4.
+roofline: the dominant kernel (asb_lists on clustered data, asb_screen otherwise) is integer-ALU bound (SURVEY 8(d));
+         see DESIGN.md section 4.
 """
 from __future__ import annotations
 
@@ -278,6 +280,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--pair-cap", type=float, default=0)
     ap.add_argument("--prune", type=int, default=1, choices=[0, 1], help="0 = switch the pivot bound off (every pair goes through the screen kernel)")
+    ap.add_argument("--param", action="append", default=[], metavar="NAME=VALUE",
+                    help="engine parameter (asb_set_param) for experiments, e.g. two_rows=0, class_sort=0, list_path=0, slab_pairs=2147483648")
     ap.add_argument("--tmpdir", default=None, help="where the e2e arm writes <stem>_compare.tmp (default: a fresh temp dir)")
     a = ap.parse_args()
     if a.reads:
@@ -314,6 +318,9 @@ def main():
     if a.pair_cap:
         facade.set_param("pair_cap", a.pair_cap)
     facade.set_param("prune", a.prune)
+    for kv in a.param:
+        name, _, val = kv.partition("=")
+        facade.set_param(name, float(val))
 
     # ---- resident-input arm -------------------------------------------------------------------
     codes_bytes = 2 * int(w["buf"].nbytes)  # forward + compl_reverse symbol codes
@@ -434,7 +441,9 @@ def main():
                        "reads": w["n_reads"], "pairs_per_step": w["tl"], "records_per_step": n_records, "mean_read_len": w["mean_len"],
                        "l2_policy": ("inputs (2 x %.0f MB symbol codes) exceed the 126 MB L2; no flush needed" % (w["buf"].nbytes / 1e6)) if flush_buf is None
                        else "inputs fit in L2: a 192 MB buffer is overwritten between timed steps",
-                       "sharding": "rows of the length-sorted batch dealt cyclically over ranks; per-slab NCCL gather of the records to rank 0 (dist.gather_step)"},
+                       "sharding": "every slab's rows split into `world` contiguous ranges of equal pair counts; each rank prints and writes its own piece "
+                                   "of the tempfile; per-slab NCCL gather of the records to rank 0 for the resident lines (dist.gather_step)",
+                       **({"params": a.param} if a.param else {})},
             "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, **parity}
     if not a.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(w, seconds=a.cpu_seconds)
