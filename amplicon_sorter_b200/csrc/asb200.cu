@@ -17,6 +17,7 @@
 //   cub radix sorts put the lists in (row, column) order so that the 32 lanes of a warp share a
 //   query, and put the emitted records in the reference's line order.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -66,6 +67,7 @@ struct DevBatch {
     int cont_thresh;
     // list task space
     const uint64_t* list; const uint32_t* list_val; uint64_t list_n;
+    const unsigned long long* list_n_dev;  // non-null: the list's length is this device counter (list_n = an upper bound the host knows)
     const uint8_t* ex_strand; int32_t* ex_out;  // M_EXACT
     int ex_hw;                                  // M_EXACT: 1 = edlib HW (infix) distance
     int ex_cap;                                 // M_EXACT: < 0 = exact distance; >= 0 = exact if <= ex_cap, else -1 ("more than ex_cap")
@@ -215,7 +217,10 @@ __device__ __forceinline__ void process_group(const DevBatch& B, uint32_t* wsm, 
     g.Dmax = Dmax;
     g.Emax = Emax;
     g.T0 = (31 + Emax) >> 5;  // rows <= 32 + Emax
-    const int need = ((Dmax + 31) >> 5) + ((Emax + 31) >> 5) + 1;
+    // window words a lane needs: its own band only (each lane keeps its registers on its own rows; the host picks the
+    // class from the same per-pair formula).  Lanes whose bands hang on opposite sides of the diagonal -- reads longer
+    // AND shorter than a consensus, or the two queries of a group -- do not add up.
+    const int need = __reduce_max_sync(0xFFFFFFFFu, ok ? ((e + max(n - m, 0) + 31) >> 5) + ((e + max(m - n, 0) + 31) >> 5) + 1 : 0);
     g.Bw = BT > 0 ? BT : min(need, max(W, 1));
     if ((BT > 0 && need > BT && W > BT) || (BT == 0 && g.Bw > kMaxDynWords)) {
         atomicOr(&B.ctr[C_ERR], (unsigned long long)E_BAND);
@@ -358,14 +363,16 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? ASB_LISTS_MINB9 : 0
     uint32_t* peq = smem + wid * B.warp_words;
     unsigned long long cols_acc = 0;
     unsigned useful_acc = 0;
-    const unsigned long long n_slices = (B.list_n + 31) >> 5;
+    // written by the kernels before this one on the stream; nobody appends to a list while it is being read
+    const unsigned long long list_n = B.list_n_dev ? *reinterpret_cast<const volatile unsigned long long*>(B.list_n_dev) : B.list_n;
+    const unsigned long long n_slices = (list_n + 31) >> 5;
     for (;;) {
         unsigned long long t = 0;
         if (lane == 0) t = atomicAdd(&B.ctr[C_TASK], 1ull);
         t = __shfl_sync(0xFFFFFFFFu, t, 0);
         if (t >= n_slices) break;
         const uint64_t e = t * 32 + lane;
-        const bool have = e < B.list_n;
+        const bool have = e < list_n;
         const uint64_t key = have ? B.list[e] : 0;
         const uint32_t myrow = (uint32_t)(key >> 32);
         const uint32_t jmask = B.jbits ? ((1u << B.jbits) - 1u) : 0x7FFFFFFFu;
@@ -481,7 +488,8 @@ __global__ void __launch_bounds__(256) asb_prune(const DevBatch B)
                     needF = !pf;
                     needR = pf && !pr;
                     // class of the TARGET (sort order inside the row only): pivot | orientation | distance bucket
-                    if (B.jbits) cls = wb == kUncovered ? (B.cls_pmask << 4) | 15u
+                    if (B.jbits && (needF || needR))
+                        cls = wb == kUncovered ? (B.cls_pmask << 4) | 15u
                                                         : ((cw_pivot(wb) & B.cls_pmask) << 4) | (cw_orient(wb) << 3) | min(7u, cw_dist(wb) / B.cls_adiv);
                 }
             }
@@ -754,8 +762,12 @@ template <typename T> struct DevBuf {
 
 }  // namespace
 
+struct LaunchShape { int warps; size_t smem; int grid; };
+struct ShapeEntry { const void* fn; int max_warps; int warp_words; LaunchShape shape; };
+
 struct asb_ctx {
     int device = 0;
+    std::vector<ShapeEntry> shapes;  // launch_cfg's cache
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::string err;
@@ -785,7 +797,7 @@ struct asb_ctx {
     DevBuf<uint8_t> d_tmp;
     uint64_t list_cap = 0;
     unsigned long long* h_ctr = nullptr;  // pinned [C_COUNT]
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[10] = {};
     // last step's sorted records on device
     uint64_t* rec_keys = nullptr; uint32_t* rec_vals = nullptr; uint64_t rec_n = 0;
     uint32_t launches = 0;  // own kernels launched since the last step began
@@ -901,29 +913,34 @@ int read_counters(asb_ctx* ctx)
     return ASB_OK;
 }
 
-struct LaunchShape { int warps; size_t smem; int grid; };
-
 // Every warp owns a Peq table of (sigma+1) x Wpad words.  8 warps per block normally; large alphabets or
 // very long reads fall back to fewer warps per block so that the tables still fit in shared memory.
+// The shape of a (kernel, layout) pair is looked up once per context: the attribute call and the occupancy query
+// are host latency in front of every launch otherwise.
 template <typename F> int launch_cfg(asb_ctx* ctx, F fn, const DevBatch& B, LaunchShape* shape, int max_warps = kWarpsPerBlock)
 {
+    for (const auto& c : ctx->shapes)
+        if (c.fn == (const void*)fn && c.max_warps == max_warps && c.warp_words == B.warp_words) { *shape = c.shape; return ASB_OK; }
     for (int warps = max_warps; warps >= 1; warps >>= 1) {
         const size_t smem = (size_t)warps * B.warp_words * sizeof(uint32_t);
         if (smem > 227 * 1024) continue;
-        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the LIMIT, once and for all layouts this kernel will run with (a cached shape must never find it lowered)
+        CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, smem));
         if (per_sm < 1) continue;
         shape->warps = warps; shape->smem = smem; shape->grid = per_sm * ctx->sm_count;
+        ctx->shapes.push_back({(const void*)fn, max_warps, B.warp_words, *shape});
         return ASB_OK;
     }
     return fail(ctx, ASB_E_TOO_LONG, "match-mask table of one query (%u symbols x %d words) does not fit in shared memory", ctx->sigma + 1, B.Wpad);
 }
 
-int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint32_t* vals, uint64_t n)
+// n_dev: the device counter holding the list's real length (n is then the host's upper bound, used to size the grid)
+int run_list(asb_ctx* ctx, DevBatch& B, int mode, int cls, uint64_t* keys, uint32_t* vals, uint64_t n, const unsigned long long* n_dev = nullptr)
 {
     if (n == 0) return ASB_OK;
-    B.list = keys; B.list_val = vals; B.list_n = n;
+    B.list = keys; B.list_val = vals; B.list_n = n; B.list_n_dev = n_dev;
     CU(cudaMemsetAsync(ctx->d_ctr.p + C_TASK, 0, sizeof(unsigned long long), ctx->stream));
     lists_fn fn = Fns::lists(cls);
     LaunchShape ls;
@@ -1314,7 +1331,7 @@ int asb_create(int device, void* stream, asb_ctx** out)
     else { e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking); ctx->own_stream = true; }
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_ctr, sizeof(unsigned long long) * C_COUNT);
-    for (int i = 0; i < 6 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 10 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = ctx->d_ctr.ensure(C_COUNT);
     if (e != cudaSuccess) { asb_destroy(ctx); return ASB_E_CUDA; }
     *out = ctx;
@@ -1341,7 +1358,7 @@ void asb_destroy(asb_ctx* ctx)
     if (ctx->tev) cudaEventDestroy(ctx->tev);
     if (ctx->h_tctr) cudaFreeHost(ctx->h_tctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
-    for (int i = 0; i < 6; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 10; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1518,48 +1535,57 @@ static int need_words(const asb_ctx* ctx, uint32_t p, const std::vector<uint32_t
 }
 
 // F -> R -> Z -> O: the list stages shared by the all-pairs step and the explicit pair-list entry point.
-// d_F holds nF unsorted keys; on return ctx->rec_keys/rec_vals/rec_n describe the sorted records.
-static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, uint64_t nF, asb_step_info* info)
+// d_F holds nF unsorted keys and the R / Z / O lists already hold cR / cZ / cO entries (appended by asb_prune or
+// asb_screen; the host read these counts once).  On return ctx->rec_keys/rec_vals/rec_n describe the sorted records.
+// The three passes and the four sorts are enqueued back to back WITHOUT reading a counter in between: the host
+// only knows upper bounds of the R / Z / O lengths (every pair sits in at most one list), so each list is padded with
+// all-ones keys up to its bound, sorted at that length (the padding sorts to the end: no row has every key bit set),
+// and the list kernel takes the real length from the device counter.  One synchronisation at the end instead of
+// four: at 8 GPUs a slab's passes are ~2 ms each, and every host round trip in between costs as much as a pass once
+// 8 processes share the host's cores.
+static int finish_lists(asb_ctx* ctx, DevBatch& B, int cls, int zcls, int wmax, uint64_t nF, uint64_t cR, uint64_t cZ, uint64_t cO,
+                        asb_step_info* info)
 {
     int rc;
     info->fwd_survivors = nF;
+    const uint64_t maxR = cR + nF, maxZ = cZ + maxR, maxO = cO + nF + cR + cZ;
+    if (std::max(maxZ, maxO) > ctx->list_cap) return fail(ctx, ASB_E_INTERNAL, "lists too small for their upper bounds");
+    if (maxR > cR) CU(cudaMemsetAsync(ctx->d_R.p + cR, 0xFF, sizeof(uint64_t) * (maxR - cR), ctx->stream));
+    if (maxZ > cZ) CU(cudaMemsetAsync(ctx->d_Z.p + cZ, 0xFF, sizeof(uint64_t) * (maxZ - cZ), ctx->stream));
+    if (maxO > cO) CU(cudaMemsetAsync(ctx->d_O.p + cO, 0xFF, sizeof(uint64_t) * (maxO - cO), ctx->stream));
     uint64_t* keys; uint32_t* vals;
-    // F: full forward pass
-    float lists_ms = 0.f, ms = 0.f;
     DevBatch BL = B;  // the list passes' own shared-memory layout (two query slots per warp)
     list_slots(ctx, BL, B.Wpad, true);
+    // F: full forward pass
     rc = sort_list(ctx, ctx->d_F.p, nullptr, nF, &keys, nullptr); if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
     rc = run_list(ctx, BL, M_FWD, cls, keys, nullptr, nF); if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[5], ctx->stream));
-    rc = read_counters(ctx); if (rc) return rc;
-    CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); lists_ms += ms;
-    const uint64_t nR = ctx->h_ctr[C_R];
-    info->rc_survivors = nR;
     // R: full compl_reverse pass
-    rc = sort_list(ctx, ctx->d_R.p, nullptr, nR, &keys, nullptr); if (rc) return rc;
-    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
-    rc = run_list(ctx, BL, M_RC, cls, keys, nullptr, nR); if (rc) return rc;
-    CU(cudaEventRecord(ctx->ev[5], ctx->stream));
-    rc = read_counters(ctx); if (rc) return rc;
-    CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); lists_ms += ms;
-    const uint64_t nZ = ctx->h_ctr[C_Z];
-    info->zone_checks = nZ;
+    rc = sort_list(ctx, ctx->d_R.p, nullptr, maxR, &keys, nullptr); if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+    rc = run_list(ctx, BL, M_RC, cls, keys, nullptr, maxR, ctx->d_ctr.p + C_R); if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev[7], ctx->stream));
     // Z: exact forward decision at drev
-    rc = sort_list(ctx, ctx->d_Z.p, ctx->d_Zv.p, nZ, &keys, &vals); if (rc) return rc;
+    rc = sort_list(ctx, ctx->d_Z.p, ctx->d_Zv.p, maxZ, &keys, &vals); if (rc) return rc;
     {
         const int zbt = kClasses[zcls];
         DevBatch BZ = B;
         list_slots(ctx, BZ, peq_stride(wmax, zbt), false);
-        CU(cudaEventRecord(ctx->ev[4], ctx->stream));
-        rc = run_list(ctx, BZ, M_ZONE, zcls, keys, vals, nZ); if (rc) return rc;
-        CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+        CU(cudaEventRecord(ctx->ev[8], ctx->stream));
+        rc = run_list(ctx, BZ, M_ZONE, zcls, keys, vals, maxZ, ctx->d_ctr.p + C_Z); if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev[9], ctx->stream));
     }
-    rc = read_counters(ctx); if (rc) return rc;
+    rc = sort_list(ctx, ctx->d_O.p, ctx->d_Ov.p, maxO, &ctx->rec_keys, &ctx->rec_vals); if (rc) return rc;
+    rc = read_counters(ctx); if (rc) return rc;  // the one synchronisation; also checks the device error flags
+    float lists_ms = 0.f, ms = 0.f;
     CU(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5])); lists_ms += ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7])); lists_ms += ms;
+    CU(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9])); lists_ms += ms;
     info->lists_ms = lists_ms;
+    info->rc_survivors = ctx->h_ctr[C_R];
+    info->zone_checks = ctx->h_ctr[C_Z];
     const uint64_t nO = ctx->h_ctr[C_O];
-    rc = sort_list(ctx, ctx->d_O.p, ctx->d_Ov.p, nO, &ctx->rec_keys, &ctx->rec_vals); if (rc) return rc;
     ctx->rec_n = nO;
     info->n_records = nO;
     info->word_updates = ctx->h_ctr[C_WORDS] * 32ull;
@@ -1575,6 +1601,10 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     memset(info, 0, sizeof *info);
     ctx->launches = 0;
     const uint32_t n = ctx->n;
+    static const bool trace = getenv("ASB200_TRACE") != nullptr;  // host-side phase times of every step on stderr
+    const auto now = [] { return std::chrono::steady_clock::now(); };
+    const auto ms_since = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t_enter = now();
     // skip rows without partners
     uint32_t r0 = ctx->next_row;
     while (r0 < n && ctx->h_hi[r0] == r0) ++r0;
@@ -1681,6 +1711,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     B.cword = ctx->d_cword.p; B.pivD = ctx->d_pivD.p; B.n_piv = ctx->cl_npiv;
     const int pgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 8, std::max<uint64_t>(((uint64_t)B.n_tasks + 8 * kPruneChunk - 1) / (8 * kPruneChunk), 1));
 
+    const auto t_setup = now();
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     bool pruned = false;
     if (try_prune && B.n_tasks) {
@@ -1749,11 +1780,14 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
         }
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    rc = read_counters(ctx);
-    if (rc) return rc;
+    if (!pruned) {  // (asb_prune's counters were read when its lists were checked)
+        rc = read_counters(ctx);
+        if (rc) return rc;
+    }
     info->screen_word_updates = ctx->h_ctr[C_WORDS] * 32ull;
     info->screen_useful_word_updates = ctx->h_ctr[C_USEFUL] * 32ull;
-    rc = finish_lists(ctx, B, cls, zcls, (int)wmax, ctx->h_ctr[C_F], info);
+    const auto t_first = now();
+    rc = finish_lists(ctx, B, cls, zcls, (int)wmax, ctx->h_ctr[C_F], ctx->h_ctr[C_R], ctx->h_ctr[C_Z], ctx->h_ctr[C_O], info);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1766,6 +1800,10 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     info->cluster_ms = ctx->cl_ms; ctx->cl_ms = 0.f;  // charged to the step that built the clusters
     info->n_pivots = pruned ? ctx->cl_npiv : 0;
     ctx->next_row = r1;
+    if (trace)
+        fprintf(stderr, "[asb200 step] rows %u..%u rank %u/%u pairs %llu: setup %.2f ms, first stage %.2f ms, lists %.2f ms (host wall); device %.2f ms\n",
+                r0, r1, ctx->rank, ctx->world, (unsigned long long)my_pairs, ms_since(t_enter, t_setup), ms_since(t_setup, t_first),
+                ms_since(t_first, now()), info->total_ms);
     return ASB_OK;
 }
 
@@ -1974,7 +2012,7 @@ int asb_threeway_pairs(asb_ctx* ctx, const uint32_t* q, const uint32_t* t, uint6
     const int bt = kClasses[cls];
     set_layout(ctx, B, peq_stride((int)wmax, bt), true);  // positions are read ids: pos_read stays null
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = finish_lists(ctx, B, cls, zcls, (int)wmax, npairs, info);
+    rc = finish_lists(ctx, B, cls, zcls, (int)wmax, npairs, 0, 0, 0, info);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

@@ -242,7 +242,7 @@ int asb_text_load(asb_ctx* ctx, const asb_record* dev_recs, uint64_t n, int sort
         CU(cudaGetLastError());
         ctx->launches++;
         ctx->t_keys = ctx->d_t_keys.p; ctx->t_vals = ctx->d_t_vals.p;
-        if (sort && n > 1) {  // per-rank lists are sorted; their union (rows dealt cyclically) is not
+        if (sort && n > 1) {  // per-rank lists are sorted; their union (compare_batch gathers rank by rank) is not
             CU(ctx->d_t_keys_alt.ensure(n)); CU(ctx->d_t_vals_alt.ensure(n));
             cub::DoubleBuffer<uint64_t> kb(ctx->d_t_keys.p, ctx->d_t_keys_alt.p);
             cub::DoubleBuffer<uint32_t> vb(ctx->d_t_vals.p, ctx->d_t_vals_alt.p);

@@ -1,9 +1,11 @@
 """One process per GPU: shard the all-pairs stage over ranks with torch.distributed.
 
 The pair set shards with no exchange step: every rank holds all reads and
-decides the rows `p % world == rank` of the sorted batch.  The only communication is
-(1) rank 0 broadcasting the job (reads + batch composition) to the workers and (2) the gather of
-the compacted per-rank record lists to rank 0 -- NCCL over NVLink on GPUs, gloo in CPU tests.
+decides its own contiguous range of the rows of every slab (ranges of equal pair counts, asb_batch_step),
+prints the lines of that range and writes them at their offset of the tempfile.  The only communication is
+(1) rank 0 broadcasting the job (reads + batch composition) to the workers, (2) one small all_gather per slab
+(record counts, status, bytes printed) and (3) the gather of the compacted per-rank record lists to rank 0,
+where they become the resident integer lines -- NCCL over NVLink on GPUs, gloo in CPU tests.
 
     torchrun --nproc-per-node 8 -m amplicon_sorter_b200 --script amplicon_sorter.py -i reads.fastq ...
 

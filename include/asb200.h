@@ -78,7 +78,11 @@ const char *asb_last_error(const asb_ctx *ctx);
 /* Tuning knobs (results never depend on them): "pair_cap", "screen_frac", "push_thresh", "cont_thresh",
  * "seed_lb" (1/0: use the admissible q-mer seed lower bound to end hopeless alignments early),
  * "prune" (1/0: decide pairs of unrelated read clusters by the triangle inequality over pivot reads; tried on jobs
- * of at least "prune_min_reads" reads and "prune_min_pairs" pairs). */
+ * of at least "prune_min_reads" reads and "prune_min_pairs" pairs),
+ * "two_rows" (1/0: a warp of the list passes takes the pairs of two queries at a time),
+ * "class_sort" (1/0: the list entries of a row are ordered by the cluster class of their target),
+ * "list_path" (1/0: clustered reads whose pairs the pivot bound cannot decide take the class-sorted list passes
+ * instead of the screen kernel), "slab_pairs" (pairs per slab over all ranks once the list path is chosen). */
 int asb_set_param(asb_ctx *ctx, const char *name, double value);
 
 /* Replaces the per-record `str(record.seq).upper()` payload (:551) + per-pair compl_reverse (:795):

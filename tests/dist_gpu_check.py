@@ -1,6 +1,6 @@
 """Multi-GPU check, run under torchrun on a GPU box (tests/test_gpu_text.py spawns it when >= 2 GPUs are visible):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/dist_gpu_check.py
-Every rank decides its cyclic shard on its own GPU; what rank 0 gathers over NCCL must equal the CPU oracle --
+Every rank decides its shard of the rows on its own GPU; what rank 0 gathers over NCCL must equal the CPU oracle --
 as records (compare_batch) and as the text of the tempfile (host.process_list on the ShardedEngine)."""
 import os
 import sys

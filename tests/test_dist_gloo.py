@@ -1,4 +1,4 @@
-"""CPU, world_size 2, gloo: the multi-rank host path (broadcast of the job, cyclic sharding, gather of
+"""CPU, world_size 2, gloo: the multi-rank host path (broadcast of the job, row sharding, gather of
 the per-rank record lists, merge on rank 0) reproduces the single-rank result and the golden file."""
 import gzip
 import json
