@@ -12,7 +12,8 @@ RECORD = np.dtype([("i_pos", "<u4"), ("j_pos", "<u4"), ("d", "<u4"), ("reverse",
 
 ASB_OK, ASB_DONE = 0, 1
 TEXT_MAX_LINE = 40  # >= kTextMaxLine of csrc/text.cuh: bytes of the longest possible line
-TEXT_CHUNK = 1 << 21  # records per asb_text_step call: bounds the pinned buffers (3 x 80 MB) and feeds the writer early
+TEXT_CHUNK = 1 << 19  # records per asb_text_step call: bounds the pinned buffers (6 x 32 MB; pinning costs ~0.3 ms per MB,
+# on the critical path of a one-shot run) and feeds the writer threads early
 
 
 class StepInfo(C.Structure):

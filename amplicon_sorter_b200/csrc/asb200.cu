@@ -825,7 +825,8 @@ struct asb_ctx {
     int class_sort = 1;         // parameter "class_sort": list entries of a row ordered by the target's cluster class (asb_prune)
     int list_path = 1;          // parameter "list_path": clustered reads whose pairs the pivot bound cannot decide still take
                                 //   the class-sorted list passes instead of the screen kernel (0 = screen kernel, as before)
-    uint64_t slab_pairs = 1ull << 30;  // parameter "slab_pairs": pairs per slab over all ranks once pruning is known to work
+    uint64_t slab_pairs = 0;    // parameter "slab_pairs": pairs per slab over all ranks once the list path is chosen; 0 = 2^30 (2^31 from
+                                //   8 ranks on: measured on one GPU as rank 0 of 8, config 5: 40.3 / 37.7 / 36.4 ms of kernels at 2^30 / 2^31 / 2^32)
     uint32_t prune_min_reads = 1024; uint64_t prune_min_pairs = 1ull << 22;  // below these a job is a few milliseconds anyway
     bool cl_ready = false; uint32_t cl_kmax = 0, cl_npiv = 0, cl_covered = 0;
     int prune_mode = 0;         // this batch: 0 = undecided, 1 = prune path, -1 = screen path
@@ -1374,7 +1375,7 @@ int asb_set_param(asb_ctx* ctx, const char* name, double value)
     else if (!strcmp(name, "two_rows")) { ctx->two_rows = value != 0; }
     else if (!strcmp(name, "class_sort")) { ctx->class_sort = value != 0; }
     else if (!strcmp(name, "list_path")) { ctx->list_path = value != 0; }
-    else if (!strcmp(name, "slab_pairs")) { if (value < 1024) return fail(ctx, ASB_E_ARG, "slab_pairs too small"); ctx->slab_pairs = (uint64_t)value; }
+    else if (!strcmp(name, "slab_pairs")) { if (value != 0 && value < 1024) return fail(ctx, ASB_E_ARG, "slab_pairs too small"); ctx->slab_pairs = (uint64_t)value; }
     else if (!strcmp(name, "prune_min_reads")) { ctx->prune_min_reads = (uint32_t)std::max(0.0, value); ctx->cl_ready = false; }
     else if (!strcmp(name, "prune_min_pairs")) { ctx->prune_min_pairs = (uint64_t)std::max(0.0, value); }
     else if (!strcmp(name, "cont_thresh")) { if (value < 0 || value > 32) return fail(ctx, ASB_E_ARG, "cont_thresh in [0,32]"); ctx->cont_thresh = (int)value; }
@@ -1632,13 +1633,14 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     const bool try_prune = ctx->prune_mode >= 0;
     // slab: rows of one window class, at most pair_cap pairs per rank.  Once the list path is chosen, a slab is sized by
     // what SURVIVES the pivot bound (at most 2^27 list entries per rank, 7 GB of lists) up to slab_pairs pairs over
-    // ALL ranks (default 2^30: with more ranks the slabs must not become fewer, or nothing is left to overlap the
-    // gather and the text of a slab with)
+    // ALL ranks (default 2^30, 2^31 from 8 ranks on: with more ranks the slabs must not become much fewer, or nothing is
+    // left to overlap the gather and the text of a slab with; but a rank's three passes of a 2^30 / 8 slab are ~2 ms each)
     uint64_t slab_cap = ctx->pair_cap;
     if (ctx->prune_mode == 1) {
         const double keep = std::max(ctx->prune_left_ratio, 1.0 / 1024.0);
         const uint64_t by_lists = (uint64_t)std::min<double>((double)(1ull << 27) / keep, 9.0e18);
-        slab_cap = std::max<uint64_t>(ctx->pair_cap, std::min<uint64_t>(ctx->slab_pairs / ctx->world, by_lists));
+        const uint64_t slab_total = ctx->slab_pairs ? ctx->slab_pairs : (ctx->world >= 8 ? 1ull << 31 : 1ull << 30);
+        slab_cap = std::max<uint64_t>(ctx->pair_cap, std::min<uint64_t>(slab_total / ctx->world, by_lists));
     }
     const int cls = class_for(std::min(need_words(ctx, r0, ctx->h_pmax_dpass, 0), (int)((ctx->h_len[r0] + 31) / 32)));
     // Every slab's rows are split into `world` CONTIGUOUS ranges of (almost) equal pair counts, rank k takes the k-th:

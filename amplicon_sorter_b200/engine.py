@@ -275,7 +275,7 @@ class Engine(EngineBase):
             if sl.ptr:
                 self._lib.asb_host_free(sl.ptr)
                 sl.ptr, sl.cap = None, 0
-            want = max(cap + cap // 2, 1 << 20)
+            want = 1 << max(20, (int(cap) - 1).bit_length())  # powers of two: a slot is re-pinned a handful of times at most
             p = C.c_void_p()
             if self._lib.asb_host_alloc(want, C.byref(p)) != 0:
                 raise EngineError(-3, f"cannot pin {want} bytes of host memory for the tempfile text")

@@ -229,15 +229,20 @@ class AllPairs:
         self.stats = {"pairs": 0, "records": 0, "fwd_survivors": 0, "rc_survivors": 0, "zone_checks": 0,
                       "word_updates": 0, "gpu_ms": 0.0, "screen_ms": 0.0}
 
-    def upload(self, seqs: list[str]):
+    def set_lengths(self, seqs: list[str]):
         lens = np.fromiter(map(len, seqs), dtype=np.uint64, count=len(seqs))
+        self.lens = lens.astype(np.int64)
+        return lens
+
+    def upload(self, seqs: list[str], lens=None):
+        if lens is None:
+            lens = self.set_lengths(seqs)
         offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
         np.cumsum(lens, out=offs[1:])
-        self._joined = "".join(seqs)  # kept alive: `buf` may be a view of it
-        buf = ascii_view(self._joined)
+        joined = "".join(seqs)  # kept alive: `buf` may be a view of it
+        buf = ascii_view(joined)
         self.engine.upload_reads(buf, offs)
-        self._joined = None
-        self.lens = lens.astype(np.int64)
+        del buf, joined
 
     def _account(self, tot):
         self.stats["pairs"] += tot["pairs"]
@@ -280,13 +285,21 @@ class AllPairs:
         tl = int((hi.astype(np.int64) - np.arange(hi.shape[0])).sum())  # the reference's tl (:684)
         return perms, order, lens_sorted, hi, tl
 
-    def compare_to_file(self, order, lens_sorted, hi, idx_sorted, similar_genes: float, out_path: str):
-        """Decide every pair of the planned batch and append the lines to `out_path` as they are produced."""
+    @staticmethod
+    def prepare_tables(lens_sorted, idx_sorted, similar_genes: float):
+        """The integer cut-offs and the iden string tables of one planned batch (pure host work)."""
         import time
 
         t0 = time.perf_counter()
         dpass, drev = thresholds.tables(similar_genes / 100, int(lens_sorted.max()) + 1)  # similarg :783
         tables = text_tables(idx_sorted, lens_sorted, dpass)
+        return dpass, drev, tables, (time.perf_counter() - t0) * 1e3
+
+    def compare_to_file(self, order, lens_sorted, hi, prep, out_path: str):
+        """Decide every pair of the planned batch and append the lines to `out_path` as they are produced."""
+        import time
+
+        dpass, drev, tables, prep_ms = prep
         t1 = time.perf_counter()
         sink = TextSink(out_path)
         try:
@@ -295,7 +308,7 @@ class AllPairs:
         finally:
             sink.close()
         t3 = time.perf_counter()
-        self.stats["phases_ms"] = {"cut-off + iden string tables": (t1 - t0) * 1e3, "all slabs (GPU)": (t2 - t1) * 1e3,
+        self.stats["phases_ms"] = {"cut-off + iden string tables": prep_ms, "all slabs (GPU)": (t2 - t1) * 1e3,
                                    "of which pivots + read assignment": tot.get("cluster_ms", 0.0), "writer thread drain": (t3 - t2) * 1e3,
                                    **{"loop: " + k: v for k, v in tot.get("host_ms", {}).items()}}
         self._account(tot)
@@ -340,17 +353,42 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
 
     t0 = time.perf_counter()
     # distinct records of all batches, keyed by their idx field (:560-561); -ra batches overlap
-    flat = [rec for d in self for rec in d]
-    keys = np.fromiter((rec[3] for rec in flat), dtype=np.int64, count=len(flat))
-    rid_to_idx, first, inv = np.unique(keys, return_index=True, return_inverse=True)  # read id = rank of the idx value
-    seqs = [flat[i][1] for i in first.tolist()]
+    from operator import itemgetter
+
+    flat = self[0] if len(self) == 1 else [rec for d in self for rec in d]
+    keys = np.fromiter(map(itemgetter(3), flat), dtype=np.int64, count=len(flat))
+    if keys.shape[0] < 2 or bool((keys[1:] > keys[:-1]).all()):  # read_file numbers the records in file order: nothing to merge
+        rid_to_idx, inv = keys, np.arange(keys.shape[0], dtype=np.int64)
+        seqs = list(map(itemgetter(1), flat))
+    else:
+        rid_to_idx, first, inv = np.unique(keys, return_index=True, return_inverse=True)  # read id = rank of the idx value
+        seqs = [flat[i][1] for i in first.tolist()]
     batch_rids = np.split(inv.astype(np.int64), np.cumsum([len(d) for d in self])[:-1]) if len(self) else []
 
     from . import groups
 
     ap = AllPairs(engine, device)
     t1 = time.perf_counter()
-    ap.upload(seqs)
+    # The upload (string join, H2D, symbol coding: the C call releases the GIL) runs beside the host's own preparation
+    # (length sort, windows, side effect (1)) when the engine is this process's own; a sharded facade broadcasts the
+    # job with collectives and stays on the calling thread.
+    lens = ap.set_lengths(seqs)
+    up = None
+    if isinstance(ap.engine, Engine):
+        import threading
+
+        box = []
+
+        def _up():
+            try:
+                ap.upload(seqs, lens)
+            except BaseException as exc:  # re-raised on the calling thread
+                box.append(exc)
+
+        up = threading.Thread(target=_up, name="asb200-upload")
+        up.start()
+    else:
+        ap.upload(seqs, lens)
     t2 = time.perf_counter()
     live = [(d, rids) for d, rids in zip(self, batch_rids) if len(d)]
     perms, order, lens_sorted, hi, tl_total = ap.plan([rids for _, rids in live])
@@ -359,14 +397,20 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
     for old, _ in groups.CACHE.values():  # lines of an earlier input file are never asked for again (:2179 deletes that file)
         old.discard()
     groups.CACHE.clear()
+    prep = ap.prepare_tables(lens_sorted, rid_to_idx[order.astype(np.int64)], args.similar_genes) if tl_total else None
+    if up is not None:
+        up.join()
+        if box:
+            raise box[0]
     t3 = time.perf_counter()
     if tl_total:
         # records come out sorted by (global i, global j) = (batch, i, j): the reference's -np 1 file order
-        ap.compare_to_file(order, lens_sorted, hi, rid_to_idx[order.astype(np.int64)], args.similar_genes, out_path)
+        ap.compare_to_file(order, lens_sorted, hi, prep, out_path)
         # the consumers of the file (SSG, update_list, read_indexes) get its lines without parsing the text
         groups.CACHE[os.path.abspath(out_path)] = (groups.DeviceLines(ap.engine), os.path.getsize(out_path))
     t4 = time.perf_counter()
-    ap.stats["phases_ms"] = {"records -> read set": (t1 - t0) * 1e3, "join + upload": (t2 - t1) * 1e3, "sort + windows": (t3 - t2) * 1e3,
+    ap.stats["phases_ms"] = {"records -> read set": (t1 - t0) * 1e3, "join + upload (threaded on one engine)": (t2 - t1) * 1e3,
+                             "sort + windows + tables, upload joined": (t3 - t2) * 1e3,
                              "compare + write": (t4 - t3) * 1e3, **ap.stats.get("phases_ms", {})}
     if stats_out is not None:
         stats_out.update(ap.stats)
