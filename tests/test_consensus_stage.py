@@ -84,6 +84,38 @@ def test_threeway_pairs_any_length_order(engine):
         assert info["pairs"] == q.shape[0] and len(want) > 10
 
 
+@pytest.mark.gpu
+def test_threeway_pairs_queries_of_very_different_lengths(engine):
+    """Adjacent rows of an explicit pair list need not be alike: a list warp may hold the pairs of a 90-base and of a
+    650-base query at the same time (two query slots), targets longer and shorter than either."""
+    rng = np.random.default_rng(78)
+    reads = []
+    for lo, hi in ((80, 100), (300, 330), (620, 680)):
+        reads += util.random_reads(rng, 60, lo, hi, families=3, err=0.06)
+    perm = rng.permutation(len(reads))
+    reads = [reads[i] for i in perm]  # read ids (= rows) in random length order
+    buf, offs = synth.pack_reads(reads)
+    engine.upload_reads(buf, offs)
+    n = len(reads)
+    q = np.repeat(np.arange(n, dtype=np.uint32), 12)
+    t = rng.integers(0, n, q.shape[0]).astype(np.uint32)
+    key = q.astype(np.uint64) << np.uint64(32) | t
+    _, first = np.unique(key, return_index=True)
+    q, t = q[np.sort(first)], t[np.sort(first)]
+    dpass, drev = thresholds.tables(0.80, 800)
+    fe = OracleEngine()
+    fe.upload_reads(buf, offs)
+    want, _ = fe.threeway_pairs(q, t, dpass, drev)
+    try:
+        for two in (1, 0):
+            engine.set_param("two_rows", two)
+            got, info = engine.threeway_pairs(q, t, dpass, drev)
+            util.assert_same_records(got, want)
+    finally:
+        engine.set_param("two_rows", 1)
+    assert len(want) > 50 and (want["reverse"] == 1).any()
+
+
 def make_todolist(seed, n=40, L=150):
     """[A1, A2, y, z] entries as comp_consensus_groups / compare_consensus spool them (AS:1275-1299)."""
     rng = np.random.default_rng(seed)

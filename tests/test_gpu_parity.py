@@ -306,7 +306,8 @@ def _force_prune(engine, on=True):
 def test_cluster_pruning_is_only_an_optimisation(engine, cfg, scale):
     """The pivot bound (asb_prune) decides pairs without aligning them; records must not depend on it.  Forced on
     for these small inputs; cfg5 / cfg4 have unrelated amplicons (most pairs pruned), cfg2 / cfg3 / cfg1 are one
-    family per length window (nothing to prune: the probe slab must hand the batch back to the screen kernel)."""
+    family per length window (nothing to prune: every pair goes through the class-sorted list passes, or -- with
+    list_path 0, see test_list_pass_layouts_do_not_change_results -- back to the screen kernel)."""
     reads, _, _ = synth.make_config(cfg, scale=scale)
     want, st = util.oracle_batch(reads)
     try:
@@ -363,3 +364,27 @@ def test_cluster_pruning_adversarial_boundaries(engine):
         _force_prune(engine, False)
         engine.set_param("pair_cap", float(1 << 26))
     assert (want["reverse"] == 1).any() and st["records"] > 1000
+
+
+@pytest.mark.parametrize("cfg,scale", [(5, 0.02), (2, 0.08), (3, 0.1), (6, 0.02)])
+def test_list_pass_layouts_do_not_change_results(engine, cfg, scale):
+    """two_rows (a list warp takes the pairs of two queries at a time), class_sort (a row's entries ordered by the
+    cluster class of their target) and list_path (clustered but unprunable data through the list passes instead of
+    the screen kernel) only change WHICH lanes share a warp: every combination gives the oracle's records, also
+    sharded and with many small slabs."""
+    reads, _, _ = synth.make_config(cfg, scale=scale)
+    reads = reads + [b"", reads[0][:40], reads[1] + reads[2]]  # an empty read, a very short and a very long one ride along
+    want, st = util.oracle_batch(reads)
+    try:
+        _force_prune(engine, True)
+        for two, cs, lp in [(1, 1, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0), (0, 0, 0)]:
+            got, tot = util.gpu_batch(engine, reads, pair_cap=1 << 15, two_rows=two, class_sort=cs, list_path=lp)
+            assert tot["pairs"] == st["pairs"]
+            util.assert_same_records(got, want)
+        parts = util.gpu_batch(engine, reads, world=3, pair_cap=1 << 15, two_rows=1, class_sort=1, list_path=1)[0]
+        util.assert_same_records(parts, want)
+    finally:
+        _force_prune(engine, False)
+        for k in ("two_rows", "class_sort", "list_path"):
+            engine.set_param(k, 1)
+        engine.set_param("pair_cap", float(1 << 26))
