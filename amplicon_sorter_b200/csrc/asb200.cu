@@ -75,6 +75,9 @@ struct DevBatch {
     // bounds of the pivot x pivot distances in both relative orientations
     const uint32_t* cword; const uint16_t* pivD; uint32_t n_piv;
     const uint32_t* pos_cw; const uint32_t* pos_k;  // per sorted position: cluster word of its read, dpass[its length]
+    // asb_prune_rows: the batch's positions grouped by cluster (keys cluster << 32 | position, sorted; cluster n_piv =
+    // reads no pivot covers) and per cluster the largest read-to-pivot distance of its members
+    const uint64_t* memb; const uint32_t* bmax; uint32_t cl_kmax;
     // seed lower bound (K2 put to work, see myers_band.cuh::SeedLB): per-read q-mer presence bitsets and the
     // seed codes of both strands, 8 per uint4 chunk, chunks of read r from seed_off[r]
     const uint32_t* qbits; const uint4* seeds_f; const uint4* seeds_r; const uint32_t* seed_off;
@@ -434,19 +437,56 @@ __device__ __forceinline__ uint32_t cw_dist(uint32_t w) { return w & 0x7FFFFu; }
 // LONGER read), so that asb_prune reads two coalesced words per pair instead of chasing order -> read -> tables
 __global__ void __launch_bounds__(256) asb_pos_tables_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ pos_len, uint32_t n,
                                                            const uint32_t* __restrict__ cword, const uint32_t* __restrict__ dpass, uint32_t table_len,
-                                                           uint32_t* __restrict__ pos_cw, uint32_t* __restrict__ pos_k)
+                                                           uint32_t* __restrict__ pos_cw, uint32_t* __restrict__ pos_k,
+                                                           uint32_t n_piv, uint64_t* __restrict__ memb, uint32_t* __restrict__ bmax)
 {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
-        pos_cw[p] = cword[order[p]];
+        const uint32_t w = cword[order[p]];
+        pos_cw[p] = w;
         const uint32_t L = pos_len[p];
         pos_k[p] = L < table_len ? dpass[L] : 0xFFFFFFFFu;  // 0xFFFFFFFF = no distance passes
+        const uint32_t c = w == 0xFFFFFFFFu ? n_piv : (w >> 20);
+        memb[p] = ((uint64_t)c << 32) | p;
+        if (w != 0xFFFFFFFFu) atomicMax(&bmax[c], w & 0x7FFFFu);
     }
 }
 
 constexpr int kPruneChunk = 16;  // tasks per grab of the shared counter (one atomic per 512 pairs)
 
+// The pivot bound on ONE pair (lane = pair; all 32 lanes must call: the appends are warp-aggregated).
 // Appends past a list's capacity are dropped and only counted (C_F / C_R keep counting): the host then retries the
 // slab with lists of the size the counters ask for.
+__device__ __forceinline__ void prune_pair(const DevBatch& B, const uint32_t row, const int m, const uint32_t wa, const uint32_t j, const bool valid)
+{
+    bool needF = false, needR = false, pr = false;
+    uint32_t cls = 0u;
+    if (valid) {
+        const int n = (int)__ldg(&B.pos_len[j]);  // n >= m: j follows row in the length order
+        const uint32_t kk = __ldg(&B.pos_k[j]);
+        const int k = kk == 0xFFFFFFFFu ? -1 : (int)kk;
+        if (n - m <= k) {  // otherwise d >= n - m > k on both strands: nothing can be emitted
+            const uint32_t wb = __ldg(&B.pos_cw[j]);
+            bool pf = false;
+            if (wa != kUncovered && wb != kUncovered) {
+                const uint32_t x = cw_orient(wa) ^ cw_orient(wb);
+                const uint16_t* d = B.pivD + (size_t)cw_pivot(wa) * 2 * B.n_piv + cw_pivot(wb);  // D[P][x][Q]
+                const int s = k + (int)cw_dist(wa) + (int)cw_dist(wb);
+                pf = (int)__ldg(d + x * B.n_piv) > s;
+                pr = (int)__ldg(d + (x ^ 1u) * B.n_piv) > s;
+            }
+            needF = !pf;
+            needR = pf && !pr;
+            // class of the TARGET (sort order inside the row only): pivot | orientation | distance bucket
+            if (B.jbits && (needF || needR))
+                cls = wb == kUncovered ? (B.cls_pmask << 4) | 15u
+                                       : ((cw_pivot(wb) & B.cls_pmask) << 4) | (cw_orient(wb) << 3) | min(7u, cw_dist(wb) / B.cls_adiv);
+        }
+    }
+    const uint64_t key = ((uint64_t)row << 32) | (cls << B.jbits) | j;
+    warp_push(needF, B.F, nullptr, &B.ctr[C_F], B.list_cap, key | (pr ? 0x80000000ull : 0ull), 0u, &B.ctr[C_OVF]);
+    warp_push(needR, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_OVF]);
+}
+
 __global__ void __launch_bounds__(256) asb_prune(const DevBatch B)
 {
     const int lane = threadIdx.x & 31;
@@ -469,34 +509,64 @@ __global__ void __launch_bounds__(256) asb_prune(const DevBatch B)
             const uint32_t gi = local / nrw;
             const uint32_t row = __ldg(&B.my_rows[r0 + local % nrw]);
             const uint32_t j = row + 1 + gi * 32 + lane;
-            bool needF = false, needR = false, pr = false;
-            uint32_t cls = 0u;
-            if (j <= __ldg(&B.hi[row])) {
-                const int m = (int)__ldg(&B.pos_len[row]), n = (int)__ldg(&B.pos_len[j]);  // n >= m: j follows row in the length order
-                const uint32_t kk = __ldg(&B.pos_k[j]);
-                const int k = kk == 0xFFFFFFFFu ? -1 : (int)kk;
-                if (n - m <= k) {  // otherwise d >= n - m > k on both strands: nothing can be emitted
-                    const uint32_t wa = __ldg(&B.pos_cw[row]), wb = __ldg(&B.pos_cw[j]);
-                    bool pf = false;
-                    if (wa != kUncovered && wb != kUncovered) {
-                        const uint32_t x = cw_orient(wa) ^ cw_orient(wb);
-                        const uint16_t* d = B.pivD + (size_t)cw_pivot(wa) * 2 * B.n_piv + cw_pivot(wb);  // D[P][x][Q]
-                        const int s = k + (int)cw_dist(wa) + (int)cw_dist(wb);
-                        pf = (int)__ldg(d + x * B.n_piv) > s;
-                        pr = (int)__ldg(d + (x ^ 1u) * B.n_piv) > s;
-                    }
-                    needF = !pf;
-                    needR = pf && !pr;
-                    // class of the TARGET (sort order inside the row only): pivot | orientation | distance bucket
-                    if (B.jbits && (needF || needR))
-                        cls = wb == kUncovered ? (B.cls_pmask << 4) | 15u
-                                                        : ((cw_pivot(wb) & B.cls_pmask) << 4) | (cw_orient(wb) << 3) | min(7u, cw_dist(wb) / B.cls_adiv);
+            prune_pair(B, row, (int)__ldg(&B.pos_len[row]), __ldg(&B.pos_cw[row]), j, j <= __ldg(&B.hi[row]));
+        }
+    }
+}
+
+// first index e in [0, n) with keys[e] >= v (keys sorted ascending)
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* __restrict__ keys, uint32_t n, uint64_t v)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&keys[mid]) < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// asb_prune_rows: the same bound, the same per-pair test, the same survivors -- but a row no longer LOOKS at every
+// partner.  One warp per row A = (P_A, o_A, a).  A whole cluster Q is skipped when even its farthest member is
+// proven on both strands:  min_x D[P_A][x][Q] > kmax + a + bmax[Q]  implies  D[P_A][x][Q] > k + a + b  for every
+// member (k <= kmax, b <= bmax[Q]), which is exactly what prune_pair would find pair by pair.  The members of the
+// other ("near") clusters that lie inside the row's window (row, hi[row]] -- two binary searches in the batch's
+// cluster-sorted position list -- get prune_pair one by one, and so do the reads no pivot covers (cluster n_piv).
+// A row whose own read is uncovered walks its whole window.  On config 5 a row has ~1 near cluster of ~500 reads
+// among 200: the pass costs what the survivors cost, not what the 5 * 10^9 pairs cost (27 ms -> < 1 ms).
+__global__ void __launch_bounds__(256) asb_prune_rows(const DevBatch B)
+{
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(&B.ctr[C_TASK], 1ull);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= B.n_my) break;
+        const uint32_t row = __ldg(&B.my_rows[t]);
+        const uint32_t hi_r = __ldg(&B.hi[row]);
+        const int m = (int)__ldg(&B.pos_len[row]);
+        const uint32_t wa = __ldg(&B.pos_cw[row]);
+        if (wa == kUncovered) {
+            for (uint32_t j0 = row + 1; j0 <= hi_r; j0 += 32) prune_pair(B, row, m, wa, j0 + lane, j0 + lane <= hi_r);
+            continue;
+        }
+        const uint16_t* d0 = B.pivD + (size_t)cw_pivot(wa) * 2 * B.n_piv;  // D[P_A][0][.], D[P_A][1][.] follows
+        const uint32_t reach = B.cl_kmax + cw_dist(wa);
+        for (uint32_t q0 = 0; q0 <= B.n_piv; q0 += 32) {
+            const uint32_t q = q0 + lane;
+            bool near = q == B.n_piv;  // the uncovered reads
+            if (q < B.n_piv) near = min((uint32_t)__ldg(d0 + q), (uint32_t)__ldg(d0 + B.n_piv + q)) <= reach + __ldg(&B.bmax[q]);
+            unsigned nm = __ballot_sync(0xFFFFFFFFu, near);
+            while (nm) {
+                const uint32_t qq = q0 + (uint32_t)(__ffs(nm) - 1);
+                nm &= nm - 1u;
+                const uint32_t e_lo = lower_bound_u64(B.memb, B.n, ((uint64_t)qq << 32) | ((uint64_t)row + 1));
+                const uint32_t e_hi = lower_bound_u64(B.memb, B.n, ((uint64_t)qq << 32) | ((uint64_t)hi_r + 1));
+                for (uint32_t e0 = e_lo; e0 < e_hi; e0 += 32) {
+                    const bool valid = e0 + lane < e_hi;
+                    const uint32_t j = valid ? (uint32_t)__ldg(&B.memb[e0 + lane]) : 0u;
+                    prune_pair(B, row, m, wa, j, valid);
                 }
             }
-            // all 32 lanes take part in the warp-aggregated appends
-            const uint64_t key = ((uint64_t)row << 32) | (cls << B.jbits) | j;
-            warp_push(needF, B.F, nullptr, &B.ctr[C_F], B.list_cap, key | (pr ? 0x80000000ull : 0ull), 0u, &B.ctr[C_OVF]);
-            warp_push(needR, B.R, nullptr, &B.ctr[C_R], B.list_cap, key, 0u, &B.ctr[C_OVF]);
         }
     }
 }
@@ -831,6 +901,8 @@ struct asb_ctx {
     bool cl_ready = false; uint32_t cl_kmax = 0, cl_npiv = 0, cl_covered = 0;
     int prune_mode = 0;         // this batch: 0 = undecided, 1 = prune path, -1 = screen path
     DevBuf<uint32_t> d_pos_cw, d_pos_k; bool pos_tables_ready = false; double prune_left_ratio = 0.0;
+    DevBuf<uint64_t> d_memb, d_memb_alt; DevBuf<uint32_t> d_bmax; const uint64_t* memb_sorted = nullptr;  // asb_prune_rows
+    int prune_rows = 1;         // parameter "prune_rows": 1 = asb_prune_rows (whole clusters skipped per row), 0 = asb_prune (every pair looked at)
     float cl_ms = 0.f;          // device + host time spent building the clusters (reported with the first step)
 };
 
@@ -1372,6 +1444,7 @@ int asb_set_param(asb_ctx* ctx, const char* name, double value)
     else if (!strcmp(name, "push_thresh")) { if (value < 0 || value > 31) return fail(ctx, ASB_E_ARG, "push_thresh in [0,31]"); ctx->push_thresh = (int)value; }
     else if (!strcmp(name, "seed_lb")) { ctx->seed_lb = value != 0; }
     else if (!strcmp(name, "prune")) { ctx->prune = value != 0; }
+    else if (!strcmp(name, "prune_rows")) { ctx->prune_rows = value != 0; }
     else if (!strcmp(name, "two_rows")) { ctx->two_rows = value != 0; }
     else if (!strcmp(name, "class_sort")) { ctx->class_sort = value != 0; }
     else if (!strcmp(name, "list_path")) { ctx->list_path = value != 0; }
@@ -1719,12 +1792,25 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     if (try_prune && B.n_tasks) {
         if (!ctx->pos_tables_ready) {
             CU(ctx->d_pos_cw.ensure(n)); CU(ctx->d_pos_k.ensure(n));
+            CU(ctx->d_memb.ensure(n)); CU(ctx->d_memb_alt.ensure(n)); CU(ctx->d_bmax.ensure(kClMaxPivots + 1));
+            CU(cudaMemsetAsync(ctx->d_bmax.p, 0, sizeof(uint32_t) * (kClMaxPivots + 1), ctx->stream));
             asb_pos_tables_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->d_order.p, ctx->d_pos_len.p, n, ctx->d_cword.p, ctx->d_dpass.p,
-                                                                                  ctx->table_len, ctx->d_pos_cw.p, ctx->d_pos_k.p);
+                                                                                  ctx->table_len, ctx->d_pos_cw.p, ctx->d_pos_k.p,
+                                                                                  ctx->cl_npiv, ctx->d_memb.p, ctx->d_bmax.p);
             CU(cudaGetLastError());
+            {   // positions grouped by cluster, ascending inside a cluster
+                cub::DoubleBuffer<uint64_t> kb(ctx->d_memb.p, ctx->d_memb_alt.p);
+                size_t tmp = 0;
+                const int end_bit = 32 + bits_for(ctx->cl_npiv);
+                CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, kb, (int64_t)n, 0, end_bit, ctx->stream));
+                CU(ctx->d_tmp.ensure(tmp));
+                CU(cub::DeviceRadixSort::SortKeys(ctx->d_tmp.p, tmp, kb, (int64_t)n, 0, end_bit, ctx->stream));
+                ctx->memb_sorted = kb.Current();
+            }
             ctx->launches++;
             ctx->pos_tables_ready = true;
         }
+        B.memb = ctx->memb_sorted; B.bmax = ctx->d_bmax.p; B.cl_kmax = ctx->cl_kmax;
         B.pos_cw = ctx->d_pos_cw.p; B.pos_k = ctx->d_pos_k.p;
         if (ctx->class_sort) {  // class bits above the column bits of the list keys (asb_prune); needs >= 5 spare bits
             const int jb = bits_for(n), cb = std::min(12, 31 - jb);
@@ -1742,7 +1828,12 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
             B.F = ctx->d_F.p; B.R = ctx->d_R.p; B.Z = ctx->d_Z.p; B.Zv = ctx->d_Zv.p; B.O = ctx->d_O.p; B.Ov = ctx->d_Ov.p;
             B.list_cap = ctx->list_cap;
             CU(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(unsigned long long) * C_COUNT, ctx->stream));
-            asb_prune<<<pgrid, 256, 0, ctx->stream>>>(B);
+            if (ctx->prune_rows) {
+                const int rgrid = (int)std::min<uint64_t>((uint64_t)ctx->sm_count * 8, std::max<uint64_t>(((uint64_t)B.n_my + 7) / 8, 1));
+                asb_prune_rows<<<rgrid, 256, 0, ctx->stream>>>(B);
+            } else {
+                asb_prune<<<pgrid, 256, 0, ctx->stream>>>(B);
+            }
             CU(cudaGetLastError());
             ctx->launches++;
             rc = read_counters(ctx);

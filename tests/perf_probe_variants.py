@@ -32,12 +32,13 @@ class CrcSink:
 
 VARIANTS = [
     ("default", {}),
+    ("prune_rows=0", {"prune_rows": 0}),
     ("two_rows=0", {"two_rows": 0}),
     ("class_sort=0", {"class_sort": 0}),
     ("list_path=0", {"list_path": 0}),
-    ("all off", {"two_rows": 0, "class_sort": 0, "list_path": 0}),
+    ("all off", {"two_rows": 0, "class_sort": 0, "list_path": 0, "prune_rows": 0}),
 ]
-DEFAULTS = {"two_rows": 1, "class_sort": 1, "list_path": 1}
+DEFAULTS = {"two_rows": 1, "class_sort": 1, "list_path": 1, "prune_rows": 1}
 
 cfgs = [int(x) for x in sys.argv[1:]] or [5, 2]
 with Engine(0) as eng:

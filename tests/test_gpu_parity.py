@@ -369,7 +369,8 @@ def test_cluster_pruning_adversarial_boundaries(engine):
 @pytest.mark.parametrize("cfg,scale", [(5, 0.02), (2, 0.08), (3, 0.1), (6, 0.02)])
 def test_list_pass_layouts_do_not_change_results(engine, cfg, scale):
     """two_rows (a list warp takes the pairs of two queries at a time), class_sort (a row's entries ordered by the
-    cluster class of their target) and list_path (clustered but unprunable data through the list passes instead of
+    cluster class of their target), prune_rows (the pivot bound skipping whole clusters per row instead of looking at
+    every pair) and list_path (clustered but unprunable data through the list passes instead of
     the screen kernel) only change WHICH lanes share a warp: every combination gives the oracle's records, also
     sharded and with many small slabs."""
     reads, _, _ = synth.make_config(cfg, scale=scale)
@@ -377,14 +378,18 @@ def test_list_pass_layouts_do_not_change_results(engine, cfg, scale):
     want, st = util.oracle_batch(reads)
     try:
         _force_prune(engine, True)
-        for two, cs, lp in [(1, 1, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0), (0, 0, 0)]:
-            got, tot = util.gpu_batch(engine, reads, pair_cap=1 << 15, two_rows=two, class_sort=cs, list_path=lp)
+        pruned = set()
+        for two, cs, lp, pr in [(1, 1, 1, 1), (0, 1, 1, 1), (1, 0, 1, 1), (1, 1, 0, 1), (0, 0, 0, 1), (1, 1, 1, 0), (0, 0, 0, 0)]:
+            got, tot = util.gpu_batch(engine, reads, pair_cap=1 << 15, two_rows=two, class_sort=cs, list_path=lp, prune_rows=pr)
             assert tot["pairs"] == st["pairs"]
             util.assert_same_records(got, want)
+            if lp == 1 or cs == 1:
+                pruned.add(tot["pruned_pairs"])
+        assert len(pruned) == 1, pruned  # asb_prune_rows (clusters skipped per row) leaves exactly the pairs asb_prune leaves
         parts = util.gpu_batch(engine, reads, world=3, pair_cap=1 << 15, two_rows=1, class_sort=1, list_path=1)[0]
         util.assert_same_records(parts, want)
     finally:
         _force_prune(engine, False)
-        for k in ("two_rows", "class_sort", "list_path"):
+        for k in ("two_rows", "class_sort", "list_path", "prune_rows"):
             engine.set_param(k, 1)
         engine.set_param("pair_cap", float(1 << 26))
