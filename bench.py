@@ -359,11 +359,19 @@ def main():
         args = types.SimpleNamespace(outputfolder=tmp, similar_genes=80.0)
         lists = [comparelist2_of(w) for _ in range(a.e2e_steps)]  # process_list sorts its batches in place: one fresh copy per step
         stats = {}
+        # every step writes a file of its own, as a run of the script does (its output folder is fresh); the previous
+        # step's 0.5 GB file is unlinked beside the next step, not inside it
+        removers = []
         region.begin()
         for s in range(a.e2e_steps):
-            host.process_list(lists[s], "bench_compare.tmp", args, engine=facade, stats_out=stats)
+            host.process_list(lists[s], f"bench_compare_{s}.tmp", args, engine=facade, stats_out=stats)
+            if s:
+                removers.append(threading.Thread(target=os.remove, args=(os.path.join(tmp, f"bench_compare_{s - 1}.tmp"),)))
+                removers[-1].start()
         t_e2e = region.end()
-        path = os.path.join(tmp, "bench_compare.tmp")
+        for t in removers:
+            t.join()
+        path = os.path.join(tmp, f"bench_compare_{a.e2e_steps - 1}.tmp")
         fbytes = os.path.getsize(path)
         with open(path, "rb") as f:
             crc = 0
