@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -854,6 +855,9 @@ struct asb_ctx {
     std::vector<uint32_t> h_rlen;
     DevBuf<uint8_t> d_cf, d_cr;
     DevBuf<uint8_t> d_up_ascii, d_up_maps; DevBuf<uint64_t> d_up_offs, d_up_roff; DevBuf<uint32_t> d_up_present;  // upload staging
+    // asb_upload_reads_scattered: per gather thread two pinned staging buffers, a copy stream and an event per buffer
+    static constexpr int kUpThreads = 4; static constexpr size_t kUpChunk = 4u << 20;
+    uint8_t* h_up[kUpThreads][2] = {}; cudaStream_t up_stream[kUpThreads] = {}; cudaEvent_t up_ev[kUpThreads][2] = {};
     // batch
     uint32_t n = 0, rank = 0, world = 1, table_len = 0;
     std::vector<uint32_t> h_len, h_hi, h_dpass, h_drev;
@@ -1427,6 +1431,10 @@ void asb_destroy(asb_ctx* ctx)
     ctx->d_la.release(); ctx->d_lb.release(); ctx->d_lm.release(); ctx->d_bh_pos.release(); ctx->d_bh_key.release(); ctx->d_bh_alt.release();
     ctx->d_bh_alt2.release(); ctx->d_bh_line.release(); ctx->d_bh_first.release();
     ctx->d_qbits.release(); ctx->d_seed_off.release(); ctx->d_order.release(); ctx->d_seeds_f.release(); ctx->d_seeds_r.release(); ctx->d_base2.release();
+    for (int t = 0; t < asb_ctx::kUpThreads; ++t) {
+        for (int b = 0; b < 2; ++b) { if (ctx->h_up[t][b]) cudaFreeHost(ctx->h_up[t][b]); if (ctx->up_ev[t][b]) cudaEventDestroy(ctx->up_ev[t][b]); }
+        if (ctx->up_stream[t]) cudaStreamDestroy(ctx->up_stream[t]);
+    }
     if (ctx->tstream) { cudaStreamSynchronize(ctx->tstream); cudaStreamDestroy(ctx->tstream); }
     if (ctx->tev) cudaEventDestroy(ctx->tev);
     if (ctx->h_tctr) cudaFreeHost(ctx->h_tctr);
@@ -1466,6 +1474,68 @@ int asb_upload_reads(asb_ctx* ctx, const uint8_t* ascii, const uint64_t* offs, u
 int asb_upload_reads_dev(asb_ctx* ctx, const uint8_t* dev_ascii, const uint64_t* offs, uint32_t n_reads)
 {
     return upload_impl(ctx, dev_ascii, true, offs, n_reads);
+}
+
+// Reads that live in n_reads separate host buffers (the str objects of the Python host's records): a few threads
+// gather them into pinned staging buffers, 4 MB at a time, and every filled buffer goes to the device on the thread's
+// own copy stream while the thread fills the other one -- the bytes are touched once on their way to the GPU.
+int asb_upload_reads_scattered(asb_ctx* ctx, const uint8_t* const* ptrs, const uint32_t* lens, uint32_t n_reads)
+{
+    if (!ctx || (n_reads && (!ptrs || !lens))) return fail(ctx, ASB_E_ARG, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<uint64_t> offs((size_t)n_reads + 1, 0);
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        if (lens[r] && !ptrs[r]) return fail(ctx, ASB_E_ARG, "read %u: null pointer", r);
+        offs[r + 1] = offs[r] + lens[r];
+    }
+    const uint64_t nbytes = offs[n_reads];
+    CU(ctx->d_up_ascii.ensure(nbytes + 1));
+    constexpr int T = asb_ctx::kUpThreads;
+    constexpr size_t CH = asb_ctx::kUpChunk;
+    for (int t = 0; t < T; ++t) {
+        if (!ctx->up_stream[t]) CU(cudaStreamCreateWithFlags(&ctx->up_stream[t], cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            if (!ctx->h_up[t][b]) CU(cudaHostAlloc((void**)&ctx->h_up[t][b], CH, cudaHostAllocDefault));
+            if (!ctx->up_ev[t][b]) CU(cudaEventCreateWithFlags(&ctx->up_ev[t][b], cudaEventDisableTiming));
+        }
+    }
+    uint8_t* const dst = ctx->d_up_ascii.p;
+    cudaError_t errs[T];
+    std::thread th[T];
+    for (int t = 0; t < T; ++t) {
+        errs[t] = cudaSuccess;
+        // thread t owns the bytes [nbytes * t / T, nbytes * (t + 1) / T) of the concatenation
+        const uint64_t b0 = nbytes / T * t, b1 = t + 1 == T ? nbytes : nbytes / T * (t + 1);
+        th[t] = std::thread([=, &offs, &errs]() {
+            cudaError_t e = cudaSetDevice(ctx->device);
+            // first read that reaches into [b0, b1)
+            uint32_t r = (uint32_t)(std::upper_bound(offs.begin(), offs.end(), b0) - offs.begin());
+            r = r ? r - 1 : 0;
+            int buf = 0;
+            bool used[2] = {false, false};
+            for (uint64_t pos = b0; pos < b1 && e == cudaSuccess; pos += CH, buf ^= 1) {
+                const uint64_t end = std::min<uint64_t>(b1, pos + CH);
+                if (used[buf]) e = cudaEventSynchronize(ctx->up_ev[t][buf]);  // its previous copy has left the buffer
+                if (e != cudaSuccess) break;
+                uint8_t* stage = ctx->h_up[t][buf];
+                uint64_t at = pos;
+                while (at < end) {
+                    while (offs[r + 1] <= at) ++r;  // (empty reads are stepped over)
+                    const uint64_t take = std::min<uint64_t>(end, offs[r + 1]) - at;
+                    memcpy(stage + (at - pos), ptrs[r] + (at - offs[r]), take);
+                    at += take;
+                }
+                e = cudaMemcpyAsync(dst + pos, stage, end - pos, cudaMemcpyHostToDevice, ctx->up_stream[t]);
+                if (e == cudaSuccess) e = cudaEventRecord(ctx->up_ev[t][buf], ctx->up_stream[t]);
+                used[buf] = true;
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->up_stream[t]);
+            errs[t] = e;
+        });
+    }
+    for (int t = 0; t < T; ++t) th[t].join();
+    for (int t = 0; t < T; ++t) CU(errs[t]);
+    return upload_impl(ctx, dst, true, offs.data(), n_reads);
 }
 
 static int upload_impl(asb_ctx* ctx, const uint8_t* ascii, bool ascii_on_device, const uint64_t* offs, uint32_t n_reads)

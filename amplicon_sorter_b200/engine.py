@@ -159,6 +159,16 @@ class Engine(EngineBase):
         self.n_reads = n
         self._lens = (offs[1:] - offs[:-1]).astype(np.uint32)
 
+    def upload_reads_scattered(self, ptrs: np.ndarray, lens: np.ndarray):
+        """upload_reads with every read in a host buffer of its own: ptrs[r] = address of read r's bytes (uint64),
+        lens[r] = its length.  The buffers must stay valid during the call (pyhost.collect borrows them from strs)."""
+        ptrs = np.ascontiguousarray(ptrs, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        n = lens.shape[0]
+        self._check(self._lib.asb_upload_reads_scattered(self._h, C.c_void_p(ptrs.ctypes.data), ptr(lens, C.c_uint32), n))
+        self.n_reads = n
+        self._lens = lens.copy()
+
     def upload_reads_tensor(self, t, offs: np.ndarray):
         """upload_reads with the read bytes already on this engine's GPU (a uint8 torch tensor)."""
         offs = np.ascontiguousarray(offs, dtype=np.uint64)

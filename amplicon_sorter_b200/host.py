@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-from . import thresholds
+from . import pyhost, thresholds
 from .engine import Engine
 
 
@@ -356,32 +356,49 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
     from operator import itemgetter
 
     flat = self[0] if len(self) == 1 else [rec for d in self for rec in d]
-    keys = np.fromiter(map(itemgetter(3), flat), dtype=np.int64, count=len(flat))
+    ap = AllPairs(engine, device)
+    own = isinstance(ap.engine, Engine)
+    fast = pyhost.collect(flat) if own else None  # one C pass: idx keys, and where every SEQ's bytes live
+    seqs = ptrs = None
+    if fast is not None:
+        keys, ptrs, lens = fast
+    else:
+        keys = np.fromiter(map(itemgetter(3), flat), dtype=np.int64, count=len(flat))
     if keys.shape[0] < 2 or bool((keys[1:] > keys[:-1]).all()):  # read_file numbers the records in file order: nothing to merge
         rid_to_idx, inv = keys, np.arange(keys.shape[0], dtype=np.int64)
-        seqs = list(map(itemgetter(1), flat))
+        if fast is None:
+            seqs = list(map(itemgetter(1), flat))
     else:
         rid_to_idx, first, inv = np.unique(keys, return_index=True, return_inverse=True)  # read id = rank of the idx value
-        seqs = [flat[i][1] for i in first.tolist()]
+        if fast is None:
+            seqs = [flat[i][1] for i in first.tolist()]
+        else:
+            ptrs, lens = ptrs[first], lens[first]
     batch_rids = np.split(inv.astype(np.int64), np.cumsum([len(d) for d in self])[:-1]) if len(self) else []
 
     from . import groups
 
-    ap = AllPairs(engine, device)
     t1 = time.perf_counter()
-    # The upload (string join, H2D, symbol coding: the C call releases the GIL) runs beside the host's own preparation
-    # (length sort, windows, side effect (1)) when the engine is this process's own; a sharded facade broadcasts the
-    # job with collectives and stays on the calling thread.
-    lens = ap.set_lengths(seqs)
+    # The upload runs beside the host's own preparation (length sort, windows, side effect (1), string tables) when the
+    # engine is this process's own: the C call releases the GIL.  With the record walker the reads go to the GPU
+    # straight from the str objects (asb_upload_reads_scattered); without it they are joined first.  A sharded facade
+    # broadcasts the job with collectives and stays on the calling thread.
+    if fast is not None:
+        ap.lens = lens.astype(np.int64)
+    else:
+        lens = ap.set_lengths(seqs)
     up = None
-    if isinstance(ap.engine, Engine):
+    if own:
         import threading
 
         box = []
 
         def _up():
             try:
-                ap.upload(seqs, lens)
+                if fast is not None:
+                    ap.engine.upload_reads_scattered(ptrs, lens)  # `flat` keeps the strs alive
+                else:
+                    ap.upload(seqs, lens)
             except BaseException as exc:  # re-raised on the calling thread
                 box.append(exc)
 

@@ -93,6 +93,10 @@ int asb_upload_reads(asb_ctx *ctx, const uint8_t *ascii, const uint64_t *offs, u
 /* Same, with the read bytes already in DEVICE memory of the context's GPU (offs stays a host array): the buffer an
  * NCCL broadcast of the job just filled on a worker rank. */
 int asb_upload_reads_dev(asb_ctx *ctx, const uint8_t *dev_ascii, const uint64_t *offs, uint32_t n_reads);
+/* Same, with every read in a host buffer of its own (read r = ptrs[r][0 .. lens[r])): what a host that keeps its reads
+ * as separate strings has (the records of comparelist2, :551-561) -- gathered through pinned staging buffers by a few
+ * threads, copied while the next buffer is filled; the caller joins nothing. */
+int asb_upload_reads_scattered(asb_ctx *ctx, const uint8_t *const *ptrs, const uint32_t *lens, uint32_t n_reads);
 
 /* Replaces process_list.queuer (:662-715) for one batch -- or for several batches laid end to end
  * (a row's window (p, hi[p]] never leaves its batch; lengths must be non-decreasing inside every window).

@@ -123,3 +123,27 @@ def test_kmer_oracle_small_cases():
     assert oracle.kmer_shared(b"ACNGT", b"ACGT", 2) == 1  # the windows over N are skipped
     s = b"ACGTTGCAAGGCTTAACCGGTT"
     assert oracle.kmer_shared(s, oracle.compl_reverse(s), 5) == oracle.kmer_shared(s, s, 5)  # strand-independent
+
+
+def test_pyhost_record_walker_matches_the_python_passes():
+    """csrc/pyhost.c hands host.process_list the idx keys and the bytes of every SEQ in one C pass; anything that is
+    not what read_file builds (amplicon_sorter.py:551-561) makes it step aside (None -> generic Python path)."""
+    import ctypes
+
+    from amplicon_sorter_b200 import pyhost
+
+    recs = [["r0", "ACGT", "u", 7], ("r1", "", "u", 9), ["r2", "ACGTNNRY" * 40, "u", 2 ** 40]]
+    got = pyhost.collect(recs)
+    assert got is not None, "libasb_pyhost.so missing: run python -m amplicon_sorter_b200.build"
+    keys, ptrs, lens = got
+    assert keys.tolist() == [7, 9, 2 ** 40] and lens.tolist() == [4, 0, 320]
+    for (_, s, _, _), p, n in zip(recs, ptrs.tolist(), lens.tolist()):
+        assert ctypes.string_at(p, n) == s.encode("ascii")
+    assert pyhost.collect([["r0", "ACGÄ", "u", 1]]) is None      # not ASCII: one byte per character does not hold
+    assert pyhost.collect([["r0", b"ACGT", "u", 1]]) is None          # not a str
+    assert pyhost.collect([["r0", "ACGT", "u", "1"]]) is None         # idx not an int
+    assert pyhost.collect([["r0", "ACGT", "u", 2 ** 70]]) is None     # idx beyond int64
+    assert pyhost.collect([["r0", "ACGT"]]) is None                   # short record
+    assert pyhost.collect(tuple(recs)) is None                        # not a list
+    k, p, n = pyhost.collect([])
+    assert k.shape == p.shape == n.shape == (0,)
