@@ -1605,6 +1605,18 @@ static int upload_impl(asb_ctx* ctx, const uint8_t* ascii, bool ascii_on_device,
     return ASB_OK;
 }
 
+// Pivot selection and read assignment for cut-off `kmax` (= the largest dpass of the coming batch) ahead of the batch:
+// a host that still has preparation of its own to do (length sort, windows, string tables) calls this right after the
+// upload, on the thread that uploaded, and the first asb_batch_step finds the clusters ready.  Optional: the step
+// builds them itself otherwise.  Does nothing when pruning is off or the read set is below "prune_min_reads".
+int asb_prepare_pruning(asb_ctx* ctx, uint32_t kmax)
+{
+    if (!ctx) return ASB_E_ARG;
+    if (!ctx->prune || ctx->n_reads < ctx->prune_min_reads || ctx->n_reads == 0) return ASB_OK;
+    CU(cudaSetDevice(ctx->device));
+    return ensure_clusters(ctx, kmax);
+}
+
 int asb_debug_read(asb_ctx* ctx, uint32_t read, int strand, uint8_t* dst, uint32_t cap)
 {
     if (!ctx || !dst || read >= ctx->n_reads) return fail(ctx, ASB_E_ARG, "bad read id");

@@ -169,6 +169,10 @@ class Engine(EngineBase):
         self.n_reads = n
         self._lens = lens.copy()
 
+    def prepare_pruning(self, kmax: int):
+        """Build the read clusters of the pivot bound now (cut-off kmax = the largest dpass of the coming batch)."""
+        self._check(self._lib.asb_prepare_pruning(self._h, int(kmax)))
+
     def upload_reads_tensor(self, t, offs: np.ndarray):
         """upload_reads with the read bytes already on this engine's GPU (a uint8 torch tensor)."""
         offs = np.ascontiguousarray(offs, dtype=np.uint64)

@@ -399,6 +399,10 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
                     ap.engine.upload_reads_scattered(ptrs, lens)  # `flat` keeps the strs alive
                 else:
                     ap.upload(seqs, lens)
+                if lens.shape[0]:  # the pivots of the pivot bound, while this thread's owner sorts and builds tables
+                    dp, _ = thresholds.tables(args.similar_genes / 100, int(lens.max()) + 1)
+                    ok = dp[dp != 0xFFFFFFFF]
+                    ap.engine.prepare_pruning(int(ok.max()) if ok.size else 0)
             except BaseException as exc:  # re-raised on the calling thread
                 box.append(exc)
 

@@ -347,9 +347,12 @@ def main():
     clocks = sampler.stop()
     value = w["tl"] * a.steps / t_res
     n_records = agg["n_records"] // a.steps
-    # own kernels: screen + list kernels (info.launches, summed over ranks) + per slab on rank 0 the text kernels
-    # (len, write; + unpack at N > 1) + one record pack per rank and slab at N > 1; cub sorts / scans are not counted
-    gpu_launches = int(agg["launches"] + agg["steps"] * (2 if world == 1 else 3 + world))
+    # own kernels: pruning / screen + list kernels (info.launches, summed over ranks) + the text kernels (length + write per
+    # chunk of TEXT_CHUNK records, at least one chunk per slab and rank) + at N > 1 one record pack per rank and slab and
+    # the line append on rank 0; cub sorts / scans are not counted
+    from amplicon_sorter_b200 import _ffi as _f
+    text_chunks = agg["n_records"] // _f.TEXT_CHUNK + agg["steps"]
+    gpu_launches = int(agg["launches"] + 2 * text_chunks + (0 if world == 1 else agg["steps"] + agg["steps"] // world))
 
     # ---- end-to-end arm: the reference-facing call, Python lists in, tempfile on disk out ----------------
     e2e, crc = None, None
