@@ -336,11 +336,14 @@ def main():
     sampler = ClockSampler(dev.index)
     sampler.start()
     agg = None
+    steps_ms = []
     region.begin()
     for _ in range(a.steps):
         if flush_buf is not None:
             flush_buf.zero_()  # inputs smaller than L2 (small configs): evict them between timed steps
+        t_job = time.perf_counter()
         tot = job()
+        steps_ms.append(round((time.perf_counter() - t_job) * 1e3, 2))
         host_ms = tot.pop("host_ms", None)
         agg = tot if agg is None else {k: agg[k] + tot[k] for k in agg}
     t_res = region.end()
@@ -446,8 +449,8 @@ def main():
                             "equivalent_tops": nominal_ops(w) * a.steps / t_res / 1e12 / max(world, 1)},
                 "hbm": {"peak_gbs": _measured_peak("hbm_gbs"), "note": "path is not HBM-bound"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": t_res / a.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u32", "data": "synthetic",
+            "ms_per_step": t_res / a.steps * 1e3, "rank0_wall_ms_of_each_step": steps_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{DESCR[a.config]}, -sg 80; one step = the whole {w['tl']}-pair job",
                        "reads": w["n_reads"], "pairs_per_step": w["tl"], "records_per_step": n_records, "mean_read_len": w["mean_len"],
                        "l2_policy": ("inputs (2 x %.0f MB symbol codes) exceed the 126 MB L2; no flush needed" % (w["buf"].nbytes / 1e6)) if flush_buf is None
