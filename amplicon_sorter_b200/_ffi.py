@@ -37,7 +37,7 @@ class EngineError(RuntimeError):
 
 _LIB = None
 
-SYMBOLS = ["asb_version", "asb_create", "asb_destroy", "asb_last_error", "asb_set_param", "asb_upload_reads", "asb_upload_reads_dev", "asb_upload_reads_scattered", "asb_prepare_pruning",
+SYMBOLS = ["asb_version", "asb_create", "asb_destroy", "asb_last_error", "asb_set_param", "asb_upload_reads", "asb_upload_reads_dev", "asb_upload_reads_scattered", "asb_prepare_pruning", "asb_uploaded_ascii_dev",
            "asb_batch_begin", "asb_batch_step", "asb_batch_records", "asb_distance_pairs", "asb_debug_read", "asb_batch_records_dev", "asb_int_peak", "asb_format_records",
            "asb_kmer_build", "asb_kmer_shared_pairs", "asb_kmer_shared_tile", "asb_threeway_pairs",
            "asb_lines_upload", "asb_lines_hist", "asb_lines_besthit", "asb_lines_besthit_fetch", "asb_components",
@@ -70,6 +70,7 @@ def load():
     L.asb_upload_reads_dev.argtypes = [vp, vp, u64p, C.c_uint32]
     L.asb_upload_reads_scattered.argtypes = [vp, vp, u32p, C.c_uint32]
     L.asb_prepare_pruning.argtypes = [vp, C.c_uint32]
+    L.asb_uploaded_ascii_dev.argtypes = [vp, C.POINTER(vp), u64p]
     L.asb_batch_begin.argtypes = [vp, u32p, C.c_uint32, u32p, u32p, u32p, C.c_uint32, C.c_uint32, C.c_uint32]
     L.asb_batch_step.argtypes = [vp, C.POINTER(StepInfo)]
     L.asb_batch_records.argtypes = [vp, vp]

@@ -1605,6 +1605,19 @@ static int upload_impl(asb_ctx* ctx, const uint8_t* ascii, bool ascii_on_device,
     return ASB_OK;
 }
 
+// The bytes of the reads as the last asb_upload_reads / asb_upload_reads_scattered left them in DEVICE memory (their
+// concatenation, staging buffer of the upload; valid until the next upload): rank 0 of a multi-GPU run broadcasts them
+// to the other ranks from there (asb_upload_reads_dev on the receiving side) without a host copy.
+int asb_uploaded_ascii_dev(asb_ctx* ctx, const uint8_t** dev_ptr, uint64_t* nbytes)
+{
+    if (!ctx || !dev_ptr || !nbytes) return ASB_E_ARG;
+    uint64_t total = 0;
+    for (uint32_t r = 0; r < ctx->n_reads; ++r) total += ctx->h_rlen[r];
+    if (total && !ctx->d_up_ascii.p) return fail(ctx, ASB_E_ARG, "the reads were uploaded from device memory: no staging copy");
+    *dev_ptr = ctx->d_up_ascii.p; *nbytes = total;
+    return ASB_OK;
+}
+
 // Pivot selection and read assignment for cut-off `kmax` (= the largest dpass of the coming batch) ahead of the batch:
 // a host that still has preparation of its own to do (length sort, windows, string tables) calls this right after the
 // upload, on the thread that uploaded, and the first asb_batch_step finds the clusters ready.  Optional: the step

@@ -198,6 +198,36 @@ class ShardedEngine(EngineBase):
         job = broadcast_job({"op": "upload", "buf": np.ascontiguousarray(buf), "offs": np.ascontiguousarray(offs)}, self.dev)
         self._guard(lambda: _upload(self.engine, job), "upload_reads")
 
+    @property
+    def scattered_ok(self):
+        return self.dev.type == "cuda"
+
+    def upload_reads_scattered(self, ptrs, lens):
+        """Engine.upload_reads_scattered on rank 0 (reads gathered from the records' own buffers straight into device
+        memory), then the device copy of the bytes is broadcast over NCCL: the host never joins the reads."""
+        import torch.distributed as dist
+
+        err, t = None, None
+        try:
+            self.engine.upload_reads_scattered(ptrs, lens)
+            t = self.engine.uploaded_ascii_tensor(self.dev)
+        except Exception as exc:  # noqa: BLE001 -- reported through the collective below
+            err = exc
+        offs = np.zeros(len(lens) + 1, dtype=np.uint64)
+        np.cumsum(np.asarray(lens, dtype=np.uint64), out=offs[1:])
+        broadcast_job({"op": "upload_dev", "ok": err is None, "nbytes": int(t.numel()) if t is not None else 0, "offs": offs}, self.dev)
+        if err is None and t.numel():
+            dist.broadcast(t, src=0)
+        try:
+            agree(err is None, self.dev, "upload_reads")
+        except DistributedAbort:
+            self.aborted = True
+            if err is not None:
+                import traceback
+
+                traceback.print_exception(err)
+            raise
+
     def set_param(self, name, value):
         broadcast_job({"op": "param", "name": name, "value": float(value)}, self.dev)
         self.engine.set_param(name, value)
@@ -257,6 +287,20 @@ def _upload(engine, job):
         engine.upload_reads(job["buf"], job["offs"])
     else:
         engine.upload_reads_tensor(job["buf"], job["offs"])
+
+
+def _upload_dev(facade, engine, job, dev):
+    """Worker side of ShardedEngine.upload_reads_scattered: receive rank 0's device copy of the read bytes."""
+    import torch
+    import torch.distributed as dist
+
+    if not job["ok"]:  # rank 0 failed before the broadcast: only the agreement is left
+        agree(True, dev, "upload_reads")
+        return
+    t = torch.empty(int(job["nbytes"]), dtype=torch.uint8, device=dev)
+    if t.numel():
+        dist.broadcast(t, src=0)
+    facade._guard(lambda: engine.upload_reads_tensor(t, job["offs"]), "upload_reads")
 
 
 def _run_shard(engine, job, dev, r, w):
@@ -437,6 +481,8 @@ def worker_loop(engine, dev):
             return
         if op == "upload":
             facade._guard(lambda: _upload(engine, job), "upload_reads")
+        elif op == "upload_dev":
+            _upload_dev(facade, engine, job, dev)
         elif op == "param":
             engine.set_param(job["name"], job["value"])
         elif op == "batch":

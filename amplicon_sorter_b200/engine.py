@@ -169,6 +169,21 @@ class Engine(EngineBase):
         self.n_reads = n
         self._lens = lens.copy()
 
+    def uploaded_ascii_tensor(self, dev):
+        """The read bytes of the last host-side upload as a uint8 torch tensor VIEW of the engine's device staging
+        buffer (valid until the next upload): what rank 0 broadcasts to the other ranks."""
+        import torch
+
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self._lib.asb_uploaded_ascii_dev(self._h, C.byref(p), C.byref(n)))
+        if not n.value:
+            return torch.empty(0, dtype=torch.uint8, device=dev)
+
+        class _View:  # zero-copy: torch reads the CUDA array interface
+            __cuda_array_interface__ = {"shape": (int(n.value),), "typestr": "|u1", "data": (int(p.value), False), "version": 2}
+
+        return torch.as_tensor(_View(), device=dev)
+
     def prepare_pruning(self, kmax: int):
         """Build the read clusters of the pivot bound now (cut-off kmax = the largest dpass of the coming batch)."""
         self._check(self._lib.asb_prepare_pruning(self._h, int(kmax)))

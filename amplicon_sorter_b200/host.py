@@ -358,7 +358,8 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
     flat = self[0] if len(self) == 1 else [rec for d in self for rec in d]
     ap = AllPairs(engine, device)
     own = isinstance(ap.engine, Engine)
-    fast = pyhost.collect(flat) if own else None  # one C pass: idx keys, and where every SEQ's bytes live
+    can_scatter = own or bool(getattr(ap.engine, "scattered_ok", False))  # (the sharded facade on GPUs; not the CPU test engines)
+    fast = pyhost.collect(flat) if can_scatter else None  # one C pass: idx keys, and where every SEQ's bytes live
     seqs = ptrs = None
     if fast is not None:
         keys, ptrs, lens = fast
@@ -408,6 +409,8 @@ def process_list(self, tempfile, args, engine: Engine | None = None, stats_out: 
 
         up = threading.Thread(target=_up, name="asb200-upload")
         up.start()
+    elif fast is not None:
+        ap.engine.upload_reads_scattered(ptrs, lens)
     else:
         ap.upload(seqs, lens)
     t2 = time.perf_counter()

@@ -97,6 +97,9 @@ int asb_upload_reads_dev(asb_ctx *ctx, const uint8_t *dev_ascii, const uint64_t 
  * as separate strings has (the records of comparelist2, :551-561) -- gathered through pinned staging buffers by a few
  * threads, copied while the next buffer is filled; the caller joins nothing. */
 int asb_upload_reads_scattered(asb_ctx *ctx, const uint8_t *const *ptrs, const uint32_t *lens, uint32_t n_reads);
+/* Where the last asb_upload_reads / asb_upload_reads_scattered left the concatenated read bytes in device memory
+ * (valid until the next upload): the source of the NCCL broadcast of the job on rank 0. */
+int asb_uploaded_ascii_dev(asb_ctx *ctx, const uint8_t **dev_ptr, uint64_t *nbytes);
 /* Optional, after an upload: pick the pivot reads and assign the reads to them for the cut-off kmax = the largest
  * dpass[] of the coming batch, while the host is still preparing that batch (the first asb_batch_step does it
  * otherwise).  No-op when "prune" is off or fewer than "prune_min_reads" reads are uploaded. */
