@@ -1800,13 +1800,16 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     }
     const bool try_prune = ctx->prune_mode >= 0;
     // slab: rows of one window class, at most pair_cap pairs per rank.  Once the list path is chosen, a slab is sized by
-    // what SURVIVES the pivot bound (at most 2^27 list entries per rank, 7 GB of lists) up to slab_pairs pairs over
-    // ALL ranks (default 2^30, 2^31 from 8 ranks on: with more ranks the slabs must not become much fewer, or nothing is
-    // left to overlap the gather and the text of a slab with; but a rank's three passes of a 2^30 / 8 slab are ~2 ms each)
+    // what SURVIVES the pivot bound: at most 2^23 list entries per rank -- the lines of a slab are printed and written
+    // while the NEXT slab is compared, so the text of the last slab is exposed (config 4 prints 62 M lines: with two
+    // slabs of 2^30 pairs half of the 1.3 GB file was written after the last kernel, 208 ms of an 835 ms call) -- up to
+    // slab_pairs pairs over ALL ranks (default 2^30, 2^31 from 8 ranks on: with more ranks the slabs must not become
+    // much fewer, or nothing is left to overlap the gather and the text of a slab with; but a rank's three passes of a
+    // 2^30 / 8 slab are ~2 ms each)
     uint64_t slab_cap = ctx->pair_cap;
     if (ctx->prune_mode == 1) {
         const double keep = std::max(ctx->prune_left_ratio, 1.0 / 1024.0);
-        const uint64_t by_lists = (uint64_t)std::min<double>((double)(1ull << 27) / keep, 9.0e18);
+        const uint64_t by_lists = (uint64_t)std::min<double>((double)(1ull << 23) / keep, 9.0e18);
         const uint64_t slab_total = ctx->slab_pairs ? ctx->slab_pairs : (ctx->world >= 8 ? 1ull << 31 : 1ull << 30);
         slab_cap = std::max<uint64_t>(ctx->pair_cap, std::min<uint64_t>(slab_total / ctx->world, by_lists));
     }
