@@ -905,6 +905,8 @@ struct asb_ctx {
     bool cl_ready = false; uint32_t cl_kmax = 0, cl_npiv = 0, cl_covered = 0;
     int prune_mode = 0;         // this batch: 0 = undecided, 1 = prune path, -1 = screen path
     DevBuf<uint32_t> d_pos_cw, d_pos_k; bool pos_tables_ready = false; double prune_left_ratio = 0.0;
+    double rec_ratio = 0.0;     // lines per pair of this batch's slabs so far (largest seen): sizes the next slab's text
+    double hint_keep_ratio = 0.0, hint_rec_ratio = 0.0;  // the same two ratios over ALL ranks (parameters, reset by asb_batch_begin)
     DevBuf<uint64_t> d_memb, d_memb_alt; DevBuf<uint32_t> d_bmax; const uint64_t* memb_sorted = nullptr;  // asb_prune_rows
     int prune_rows = 1;         // parameter "prune_rows": 1 = asb_prune_rows (whole clusters skipped per row), 0 = asb_prune (every pair looked at)
     float cl_ms = 0.f;          // device + host time spent building the clusters (reported with the first step)
@@ -1453,6 +1455,8 @@ int asb_set_param(asb_ctx* ctx, const char* name, double value)
     else if (!strcmp(name, "seed_lb")) { ctx->seed_lb = value != 0; }
     else if (!strcmp(name, "prune")) { ctx->prune = value != 0; }
     else if (!strcmp(name, "prune_rows")) { ctx->prune_rows = value != 0; }
+    else if (!strcmp(name, "slab_keep_ratio")) { ctx->hint_keep_ratio = std::max(0.0, value); }
+    else if (!strcmp(name, "slab_rec_ratio")) { ctx->hint_rec_ratio = std::max(0.0, value); }
     else if (!strcmp(name, "two_rows")) { ctx->two_rows = value != 0; }
     else if (!strcmp(name, "class_sort")) { ctx->class_sort = value != 0; }
     else if (!strcmp(name, "list_path")) { ctx->list_path = value != 0; }
@@ -1689,6 +1693,8 @@ int asb_batch_begin(asb_ctx* ctx, const uint32_t* order, uint32_t n, const uint3
     ctx->prune_mode = 0;
     ctx->pos_tables_ready = false;
     ctx->prune_left_ratio = 0.0;
+    ctx->rec_ratio = 0.0;
+    ctx->hint_keep_ratio = ctx->hint_rec_ratio = 0.0;
     return ASB_OK;
 }
 
@@ -1800,18 +1806,24 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     }
     const bool try_prune = ctx->prune_mode >= 0;
     // slab: rows of one window class, at most pair_cap pairs per rank.  Once the list path is chosen, a slab is sized by
-    // what SURVIVES the pivot bound: at most 2^23 list entries per rank -- the lines of a slab are printed and written
-    // while the NEXT slab is compared, so the text of the last slab is exposed (config 4 prints 62 M lines: with two
-    // slabs of 2^30 pairs half of the 1.3 GB file was written after the last kernel, 208 ms of an 835 ms call) -- up to
+    // what SURVIVES the pivot bound (at most 2^27 list entries per rank, 7 GB of lists) and by what it PRINTS (at most
+    // ~2^23 lines per rank, from the lines per pair seen so far: the lines of a slab are printed and written while the
+    // NEXT slab is compared, so the text of the last slab is exposed -- config 4 prints 62 M lines, and with two slabs
+    // of 2^30 pairs half of its 1.3 GB file was written after the last kernel, 208 ms of an 835 ms call), up to
     // slab_pairs pairs over ALL ranks (default 2^30, 2^31 from 8 ranks on: with more ranks the slabs must not become
     // much fewer, or nothing is left to overlap the gather and the text of a slab with; but a rank's three passes of a
-    // 2^30 / 8 slab are ~2 ms each)
+    // 2^30 / 8 slab are ~2 ms each).  More slabs than that cost ~1.5 ms each (config 6: 31 instead of 6 slabs, + 5 %).
     uint64_t slab_cap = ctx->pair_cap;
     if (ctx->prune_mode == 1) {
-        const double keep = std::max(ctx->prune_left_ratio, 1.0 / 1024.0);
-        const uint64_t by_lists = (uint64_t)std::min<double>((double)(1ull << 23) / keep, 9.0e18);
+        // Every rank must cut the SAME slabs.  A single rank sizes them from its own counts; with more ranks the two
+        // ratios come from outside ("slab_keep_ratio" / "slab_rec_ratio": dist.py sets them on every rank from the
+        // counts all ranks exchanged for the previous slab) and are inactive (0) until then.
+        const double keep = std::max(ctx->world == 1 ? ctx->prune_left_ratio : ctx->hint_keep_ratio, 1.0 / 1024.0);
+        const double recs = std::max(ctx->world == 1 ? ctx->rec_ratio : ctx->hint_rec_ratio, 1e-9);
+        const uint64_t by_lists = (uint64_t)std::min<double>((double)(1ull << 27) / keep, 9.0e18);
+        const uint64_t by_text = (uint64_t)std::min<double>((double)(1ull << 23) / recs, 9.0e18);
         const uint64_t slab_total = ctx->slab_pairs ? ctx->slab_pairs : (ctx->world >= 8 ? 1ull << 31 : 1ull << 30);
-        slab_cap = std::max<uint64_t>(ctx->pair_cap, std::min<uint64_t>(slab_total / ctx->world, by_lists));
+        slab_cap = std::max<uint64_t>(ctx->pair_cap, std::min<uint64_t>({slab_total / ctx->world, by_lists, by_text}));
     }
     const int cls = class_for(std::min(need_words(ctx, r0, ctx->h_pmax_dpass, 0), (int)((ctx->h_len[r0] + 31) / 32)));
     // Every slab's rows are split into `world` CONTIGUOUS ranges of (almost) equal pair counts, rank k takes the k-th:
@@ -1990,6 +2002,7 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
     info->launches = ctx->launches;
     info->cluster_ms = ctx->cl_ms; ctx->cl_ms = 0.f;  // charged to the step that built the clusters
     info->n_pivots = pruned ? ctx->cl_npiv : 0;
+    ctx->rec_ratio = std::max(ctx->rec_ratio, (double)info->n_records / (double)std::max<uint64_t>(my_pairs, 1));
     ctx->next_row = r1;
     if (trace)
         fprintf(stderr, "[asb200 step] rows %u..%u rank %u/%u pairs %llu: setup %.2f ms, first stage %.2f ms, lists %.2f ms (host wall); device %.2f ms\n",

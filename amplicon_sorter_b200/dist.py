@@ -118,22 +118,24 @@ def agree(ok: bool, dev, what: str = ""):
         raise DistributedAbort(f"amplicon_sorter_b200: rank {dist.get_rank()}: a rank failed in {what or 'a sharded call'}; aborting all ranks")
 
 
-def gather_step(mine, status: int, done: bool, dev, extra: int = 0):
+def gather_step(mine, status: int, done: bool, dev, extra: int = 0, counts=(0, 0)):
     """Per-slab K6: the ranks' record tensors ((k, 4) int32 on `dev`, each sorted) -> their concatenation in rank order
     on rank 0 (None elsewhere), all on the device: counts all_gather, padded gather over NCCL / NVLink, no host round
     trip.  The counts message also carries every rank's status and done flag, so that a failed rank (or ranks that
     disagree on the number of slabs) stops ALL ranks at the same step instead of leaving them parked in a collective --
-    and one more integer per rank (`extra`: the bytes its piece of the slab prints to).
-    Returns (records on rank 0 | None, done, list of every rank's extra)."""
+    and three more integers per rank (`extra`: the bytes its piece of the slab prints to; `counts`: its pairs and its
+    list entries, for the slab-size hints every rank derives from the same totals).
+    Returns (records on rank 0 | None, done, list of every rank's extra); the per-rank heads stay in gather_step.heads."""
     import torch
     import torch.distributed as dist
 
     w, r = dist.get_world_size(), dist.get_rank()
     n = int(mine.shape[0]) if mine is not None else 0
-    head = torch.tensor([n, int(status), int(bool(done)), int(extra)], dtype=torch.int64, device=dev)
-    heads = torch.empty((w, 4), dtype=torch.int64, device=dev)
+    head = torch.tensor([n, int(status), int(bool(done)), int(extra), int(counts[0]), int(counts[1])], dtype=torch.int64, device=dev)
+    heads = torch.empty((w, 6), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(heads, head) if dev.type == "cuda" else dist.all_gather(list(heads.unbind(0)), head)
     heads = heads.tolist()
+    gather_step.heads = heads
     if any(h[1] for h in heads):
         bad = [i for i, h in enumerate(heads) if h[1]]
         raise DistributedAbort(f"amplicon_sorter_b200: rank {r}: engine failure on rank(s) {bad}; aborting all ranks")
@@ -353,6 +355,7 @@ def _run_shard_text(engine, job, dev, r, w, sink):
         traceback.print_exc()
         status = 1
     n_rec, file_pos = 0, int(job["base"])
+    g_pairs = g_left = g_recs = 0
     submit, pending = engine._text_async(my_sink, append_lines=False), None
     try:
         while True:
@@ -373,9 +376,18 @@ def _run_shard_text(engine, job, dev, r, w, sink):
 
                     traceback.print_exc()
                     status = 1
-            merged, done, sizes = gather_step(mine, status, info is None, dev, nbytes)  # raises DistributedAbort on every rank if any failed
+            counts = (info.get("pairs", 0), info.get("pairs", 0) - info.get("pruned_pairs", 0)) if info is not None else (0, 0)
+            merged, done, sizes = gather_step(mine, status, info is None, dev, nbytes, counts)  # raises DistributedAbort on every rank if any failed
             if done:
                 break
+            # the next slab's size: lines and list entries per pair over ALL ranks so far -- the same numbers on every rank
+            # (each rank's own counts would cut different slabs)
+            g_pairs += sum(h[4] for h in gather_step.heads)
+            g_left += sum(h[5] for h in gather_step.heads)
+            g_recs += sum(h[0] for h in gather_step.heads)
+            if not status and g_pairs:
+                engine.set_param("slab_keep_ratio", g_left / g_pairs)
+                engine.set_param("slab_rec_ratio", g_recs / g_pairs)
             for k in TOTALS:
                 tot[k] += info.get(k, 0)
             tot["steps"] += 1

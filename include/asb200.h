@@ -82,7 +82,9 @@ const char *asb_last_error(const asb_ctx *ctx);
  * "two_rows" (1/0: a warp of the list passes takes the pairs of two queries at a time),
  * "class_sort" (1/0: the list entries of a row are ordered by the cluster class of their target),
  * "list_path" (1/0: clustered reads whose pairs the pivot bound cannot decide take the class-sorted list passes
- * instead of the screen kernel), "slab_pairs" (pairs per slab over all ranks once the list path is chosen). */
+ * instead of the screen kernel), "slab_pairs" (pairs per slab over all ranks once the list path is chosen),
+ * "slab_keep_ratio" / "slab_rec_ratio" (multi-rank runs only, reset by asb_batch_begin: list entries and lines per
+ * pair over ALL ranks so far -- every rank must be given the same values, they size the next slab). */
 int asb_set_param(asb_ctx *ctx, const char *name, double value);
 
 /* Replaces the per-record `str(record.seq).upper()` payload (:551) + per-pair compl_reverse (:795):
