@@ -359,8 +359,14 @@ __global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? 4 : 1) asb_screen(c
 #ifndef ASB_WIDE_WARPS
 #define ASB_WIDE_WARPS 4  // measured (cfg5, zone pass): 4-warp blocks + the 20-word class 412 ms vs 458 ms per job
 #endif
+// Wide windows (BT >= 17) run ASB_WIDE_WARPS-warp blocks and are bound by their registers: the launch bounds name the
+// blocks per SM the compiler should make room for (ASB_LISTS_WIDE32: the 32-word class, 1.8 kb reads' zone pass).
+#ifndef ASB_LISTS_WIDE32
+#define ASB_LISTS_WIDE32 3  // measured (config 2, 1.8 kb reads): 161.2 / 157.3 / 163.8 ms per job at 0 (209 registers) / 3 (168) / 4 (128, spills)
+#endif
 template <int BT>
-__global__ void __launch_bounds__(256, (BT > 0 && BT <= 9) ? ASB_LISTS_MINB9 : 0) asb_lists(const DevBatch B, const int mode)
+__global__ void __launch_bounds__((BT >= 17 ? ASB_WIDE_WARPS * 32 : 256),
+                                  (BT > 0 && BT <= 9) ? ASB_LISTS_MINB9 : (BT == 32 ? ASB_LISTS_WIDE32 : 0)) asb_lists(const DevBatch B, const int mode)
 {
     extern __shared__ uint32_t smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
