@@ -142,7 +142,7 @@ class TextSink:
     with pwrite -- one thread copies ~1.5 GB/s into the page cache, a 540 MB tempfile needs several.
     Callable: sink(chunk)."""
 
-    THREADS = 4
+    THREADS = int(os.environ.get("ASB200_WRITER_THREADS", "4"))
 
     def __init__(self, path: str, existing: bool = False):
         import queue
