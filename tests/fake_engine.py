@@ -85,6 +85,20 @@ class OracleEngine(EngineBase):
         self.buf = np.array(buf, dtype=np.uint8)    # "buffers are caller-owned and copied during the call" (asb200.h)
         self.offs = np.array(offs, dtype=np.uint64)
 
+    # the scattered upload of the product engine: lets the CPU tests drive host.process_list's record walker path
+    # (pyhost.collect -> pointers into the records' own str objects) end to end
+    scattered_ok = True
+
+    def upload_reads_scattered(self, ptrs, lens):
+        import ctypes
+
+        lens = np.asarray(lens, dtype=np.uint64)
+        offs = np.zeros(lens.shape[0] + 1, dtype=np.uint64)
+        np.cumsum(lens, out=offs[1:])
+        blob = b"".join(ctypes.string_at(int(p), int(n)) for p, n in zip(np.asarray(ptrs).tolist(), lens.tolist()))
+        self.upload_reads(np.frombuffer(blob, dtype=np.uint8), offs)
+        self.scattered_uploads = getattr(self, "scattered_uploads", 0) + 1
+
     def set_param(self, *a):
         pass
 

@@ -78,10 +78,28 @@ def test_oracle_reproduces_reference_file(path):
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p) for p in FIXTURES])
 def test_host_stage_with_oracle_engine_reproduces_reference_file(path, tmp_path):
     fx = load(path)
-    text, batches, stats = run_host(fx, tmp_path, OracleEngine())
+    eng = OracleEngine()
+    text, batches, stats = run_host(fx, tmp_path, eng)
     assert text == fx["compare_tmp"]
     # side effect (1): batches left length-sorted in place, in the reference's stable order
     assert [[rec[3] for rec in b] for b in batches] == fx["batches_after"]
+    # the reads went up through the record walker (csrc/pyhost.c): pointers into the records' own str objects, merged
+    # by idx for the overlapping -ra batches
+    assert getattr(eng, "scattered_uploads", 0) == 1
+
+
+@pytest.mark.parametrize("path", FIXTURES[:1], ids=[os.path.basename(p) for p in FIXTURES[:1]])
+def test_host_stage_without_the_record_walker_is_the_same(path, tmp_path, monkeypatch):
+    """Records the walker does not handle (or a missing helper library) take the generic Python path: same file."""
+    from amplicon_sorter_b200 import pyhost
+
+    monkeypatch.setattr(pyhost, "collect", lambda records: None)
+    fx = load(path)
+    eng = OracleEngine()
+    text, batches, stats = run_host(fx, tmp_path, eng)
+    assert text == fx["compare_tmp"]
+    assert [[rec[3] for rec in b] for b in batches] == fx["batches_after"]
+    assert getattr(eng, "scattered_uploads", 0) == 0
 
 
 @pytest.mark.gpu
