@@ -5,17 +5,21 @@
 // (edlib NW distance), compl_reverse :236-241.
 //
 // Pipeline per slab of rows ("step"):
-//   asb_screen   every kept pair (i<j<=hi[i]): banded pass (k = dpass[len_j]) on the forward strand
-//                with early termination; pairs proven d_fwd > dpass get the same pass on the
+//   asb_prune_rows  (clustered read sets) the pivot bound: a row skips every cluster whose farthest member is proven
+//                > dpass on both strands and tests the members of the others; what it cannot decide goes to the
+//                F / R lists, ordered inside a row by the cluster class of the target.
+//   asb_screen   (no cluster structure, small jobs) every kept pair (i<j<=hi[i]): banded pass (k = dpass[len_j]) on the
+//                forward strand with early termination; pairs proven d_fwd > dpass get the same pass on the
 //                compl_reverse strand.  Undecided pairs go to the F / R lists.
 //   asb_lists    F: full forward pass  -> emit, or (d_fwd > dpass) -> R
 //                R: full reverse pass  -> (d_rc <= dpass) -> Z
 //                Z: forward pass with k = drev-1 -> emit ':reverse' iff d_fwd >= drev
+//                (two queries per warp; the three passes and their sorts are enqueued without host round trips)
 //   The reference decides "iden_fwd < 0.5" BEFORE trying the reverse strand; we try the (cheap)
 //   reverse strand first and only pay for the exact forward decision on the few pairs where it
 //   can change the output.  The emitted set is identical by construction.
-//   cub radix sorts put the lists in (row, column) order so that the 32 lanes of a warp share a
-//   query, and put the emitted records in the reference's line order.
+//   cub radix sorts put the lists in (row, class, column) order so that the 32 lanes of a warp share a
+//   query and behave alike, and put the emitted records in the reference's line order.
 #include <algorithm>
 #include <chrono>
 #include <cstdarg>
