@@ -1967,7 +1967,9 @@ int asb_batch_step(asb_ctx* ctx, asb_step_info* info)
         // the probe slab decides for the batch: the bound pays when it decides most pairs; when it does not, the reads
         // still have cluster classes (ensure_clusters covered most of them), and the class-sorted list passes keep the
         // lanes of a warp alike where the screen kernel's 32 consecutive targets are a mix of species and strands
-        if (ctx->prune_mode == 0) ctx->prune_mode = (2 * left <= my_pairs || (ctx->list_path && ctx->class_sort)) ? 1 : -1;
+        // (with several ranks the choice must not depend on a rank's own share of the probe slab -- the ranks would cut
+        // different slabs: they all take the list path)
+        if (ctx->prune_mode == 0) ctx->prune_mode = (2 * left <= my_pairs || (ctx->list_path && ctx->class_sort) || ctx->world > 1) ? 1 : -1;
         if (ctx->prune_mode == 1) {
             pruned = true;
             info->pruned_pairs = my_pairs - left;
