@@ -397,7 +397,9 @@ def main():
             shutil.rmtree(tmp, ignore_errors=True)
         small = w["order"].nbytes + w["hi"].nbytes + w["dpass"].nbytes + w["drev"].nbytes
         e2e = {"value": w["tl"] * a.e2e_steps / t_e2e, "unit": UNIT,
-               "h2d_bytes_per_step": int((w["buf"].nbytes + w["offs"].nbytes + small) * world + sum(np.asarray(t).nbytes if not isinstance(t, bytes) else len(t) for t in w["tables"])),
+               # the read bytes go host -> device once (rank 0; the other ranks receive rank 0's device copy over NCCL), the
+               # batch geometry, cut-off tables and iden string tables on every rank
+               "h2d_bytes_per_step": int(w["buf"].nbytes + (w["offs"].nbytes + small + sum(np.asarray(t).nbytes if not isinstance(t, bytes) else len(t) for t in w["tables"])) * world),
                "d2h_bytes_per_step": int(fbytes), "steps": a.e2e_steps, "ms_per_step": t_e2e / a.e2e_steps * 1e3,
                "tempfile_bytes": int(fbytes), "tempfile_crc32": crc,
                "rank0_phases_ms_last_step": {k: round(v, 1) for k, v in stats.get("phases_ms", {}).items()},
